@@ -1,0 +1,324 @@
+// fft_engine.cuh -- register-resident mixed-radix Stockham engine (compile-time N).
+//
+// Replaces the cuFFT plans of the reference (src/accfft_gpu.cpp:173-323: fplan_0/1/2, iplan_0, ...).
+// Everything in this header is __host__ __device__ so that tests/emul can run the *same* index math
+// under a CPU fiber emulator (test infrastructure only; the product has no CPU path).
+//
+// Algorithm: Stockham autosort, pass p with radix R_p and Ns_p = prod_{q<p} R_q:
+//     butterfly j in [0, N/R):  v[r] = x[j + r*N/R] * W_N^{ r * (j % Ns) * N/(Ns*R) }
+//                               v    = DFT_R(v)
+//                               y[(j/Ns)*Ns*R + (j%Ns) + r*Ns] = v[r]
+// A column (one 1-D transform) is worked on by G threads; thread t owns butterflies t, t+G, ...
+// The first pass reads its operands straight from global memory and the last pass writes straight
+// to global memory (both are "thread-consecutive, register-strided by N/R" => coalesced);
+// only the exchanges between passes go through shared memory.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ACC_HD __host__ __device__ __forceinline__
+#else
+#define ACC_HD inline __attribute__((always_inline))
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define ACC_UNROLL _Pragma("unroll")
+#else
+#define ACC_UNROLL
+#endif
+
+namespace accfft_b200 {
+
+template <class T>
+struct alignas(2 * sizeof(T)) cplx {
+  T x, y;
+};
+
+template <class T> ACC_HD cplx<T> cadd(cplx<T> a, cplx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <class T> ACC_HD cplx<T> csub(cplx<T> a, cplx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <class T> ACC_HD cplx<T> cmul(cplx<T> a, cplx<T> b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <class T> ACC_HD cplx<T> cconj(cplx<T> a) { return {a.x, -a.y}; }
+template <class T> ACC_HD cplx<T> cswap(cplx<T> a) { return {a.y, a.x}; }
+template <class T> ACC_HD cplx<T> cmul_mi(cplx<T> a) { return {a.y, -a.x}; }   // a * (-i)
+template <class T> ACC_HD cplx<T> cmul_pi(cplx<T> a) { return {-a.y, a.x}; }   // a * (+i)
+template <class T> ACC_HD cplx<T> cscale(cplx<T> a, T s) { return {a.x * s, a.y * s}; }
+
+// ---- compile-time roots of unity W_R^k = exp(-2 pi i k / R) for the in-register composites ----
+// (literal constants, 21 significant digits)
+// generic accessor through a constexpr switch so device code folds it into immediates
+constexpr double kC8 = 0.707106781186547524401;      // cos(pi/4)
+constexpr double kC16 = 0.923879532511286756128;     // cos(pi/8)
+constexpr double kS16 = 0.382683432365089771728;     // sin(pi/8)
+constexpr double kS3 = 0.866025403784438646764;      // sin(pi/3)
+constexpr double kC5a = 0.309016994374947424102;     // cos(2pi/5)
+constexpr double kS5a = 0.951056516295153572116;     // sin(2pi/5)
+constexpr double kC5b = -0.809016994374947424102;    // cos(4pi/5)
+constexpr double kS5b = 0.587785252292473129169;     // sin(4pi/5)
+
+constexpr double root_re(int R, int k) {
+  // cos(2 pi k / R) for the (R,k) pairs the composites need
+  k %= R;
+  if (k == 0) return 1.0;
+  if (2 * k == R) return -1.0;
+  if (4 * k == R || 4 * k == 3 * R) return 0.0;
+  if (8 * k == R || 8 * k == 7 * R) return kC8;
+  if (8 * k == 3 * R || 8 * k == 5 * R) return -kC8;
+  if (16 * k == R || 16 * k == 15 * R) return kC16;
+  if (16 * k == 7 * R || 16 * k == 9 * R) return -kC16;
+  if (16 * k == 3 * R || 16 * k == 13 * R) return kS16;
+  if (16 * k == 5 * R || 16 * k == 11 * R) return -kS16;
+  if (6 * k == R || 6 * k == 5 * R) return 0.5;
+  if (3 * k == R || 3 * k == 2 * R) return -0.5;
+  if (12 * k == R || 12 * k == 11 * R) return kS3;
+  if (12 * k == 5 * R || 12 * k == 7 * R) return -kS3;
+  return 1e300;  // unsupported -> poison (tests catch it)
+}
+constexpr double root_im(int R, int k) {
+  // -sin(2 pi k / R)
+  k %= R;
+  if (k == 0 || 2 * k == R) return 0.0;
+  if (4 * k == R) return -1.0;
+  if (4 * k == 3 * R) return 1.0;
+  if (8 * k == R || 8 * k == 3 * R) return -kC8;
+  if (8 * k == 5 * R || 8 * k == 7 * R) return kC8;
+  if (16 * k == R || 16 * k == 7 * R) return -kS16;
+  if (16 * k == 9 * R || 16 * k == 15 * R) return kS16;
+  if (16 * k == 3 * R || 16 * k == 5 * R) return -kC16;
+  if (16 * k == 11 * R || 16 * k == 13 * R) return kC16;
+  if (6 * k == R || 3 * k == R) return -kS3;
+  if (3 * k == 2 * R || 6 * k == 5 * R) return kS3;
+  if (12 * k == R || 12 * k == 5 * R) return -0.5;
+  if (12 * k == 7 * R || 12 * k == 11 * R) return 0.5;
+  return 1e300;
+}
+
+// multiply by the compile-time root W_R^K, using the cheap forms for multiples of 1/8 turn
+template <int R, int K, class T>
+ACC_HD cplx<T> mul_root(cplx<T> a) {
+  constexpr int k = ((K % R) + R) % R;
+  if constexpr (k == 0) return a;
+  else if constexpr (2 * k == R) return {-a.x, -a.y};
+  else if constexpr (4 * k == R) return cmul_mi(a);
+  else if constexpr (4 * k == 3 * R) return cmul_pi(a);
+  else if constexpr (8 * k == R) return {(a.x + a.y) * T(kC8), (a.y - a.x) * T(kC8)};          // (1-i)/sqrt2
+  else if constexpr (8 * k == 3 * R) return {(a.y - a.x) * T(kC8), -(a.x + a.y) * T(kC8)};     // (-1-i)/sqrt2
+  else if constexpr (8 * k == 5 * R) return {-(a.x + a.y) * T(kC8), (a.x - a.y) * T(kC8)};     // (-1+i)/sqrt2
+  else if constexpr (8 * k == 7 * R) return {(a.x - a.y) * T(kC8), (a.x + a.y) * T(kC8)};      // (1+i)/sqrt2
+  else {
+    constexpr double wr = root_re(R, k), wi = root_im(R, k);
+    return {a.x * T(wr) - a.y * T(wi), a.x * T(wi) + a.y * T(wr)};
+  }
+}
+
+// ---- small forward DFTs (sign -1), in place on v[0], v[S], v[2S], ... --------------------------
+template <int R, int S, class T> struct Dft;
+
+template <int S, class T> struct Dft<1, S, T> {
+  static ACC_HD void run(cplx<T>*) {}
+};
+template <int S, class T> struct Dft<2, S, T> {
+  static ACC_HD void run(cplx<T>* v) {
+    cplx<T> a = v[0], b = v[S];
+    v[0] = cadd(a, b);
+    v[S] = csub(a, b);
+  }
+};
+template <int S, class T> struct Dft<3, S, T> {
+  static ACC_HD void run(cplx<T>* v) {
+    cplx<T> a0 = v[0], a1 = v[S], a2 = v[2 * S];
+    cplx<T> t1 = cadd(a1, a2);
+    cplx<T> t2 = {a0.x - T(0.5) * t1.x, a0.y - T(0.5) * t1.y};
+    cplx<T> t3 = cscale(csub(a1, a2), T(kS3));
+    v[0] = cadd(a0, t1);
+    v[S] = {t2.x + t3.y, t2.y - t3.x};
+    v[2 * S] = {t2.x - t3.y, t2.y + t3.x};
+  }
+};
+template <int S, class T> struct Dft<4, S, T> {
+  static ACC_HD void run(cplx<T>* v) {
+    cplx<T> a0 = v[0], a1 = v[S], a2 = v[2 * S], a3 = v[3 * S];
+    cplx<T> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmul_mi(csub(a1, a3));
+    v[0] = cadd(t0, t2);
+    v[S] = cadd(t1, t3);
+    v[2 * S] = csub(t0, t2);
+    v[3 * S] = csub(t1, t3);
+  }
+};
+template <int S, class T> struct Dft<5, S, T> {
+  static ACC_HD void run(cplx<T>* v) {
+    cplx<T> a0 = v[0], a1 = v[S], a2 = v[2 * S], a3 = v[3 * S], a4 = v[4 * S];
+    cplx<T> s1 = cadd(a1, a4), d1 = csub(a1, a4), s2 = cadd(a2, a3), d2 = csub(a2, a3);
+    v[0] = {a0.x + s1.x + s2.x, a0.y + s1.y + s2.y};
+    cplx<T> p1 = {a0.x + T(kC5a) * s1.x + T(kC5b) * s2.x, a0.y + T(kC5a) * s1.y + T(kC5b) * s2.y};
+    cplx<T> p2 = {a0.x + T(kC5b) * s1.x + T(kC5a) * s2.x, a0.y + T(kC5b) * s1.y + T(kC5a) * s2.y};
+    // q = -i * (sin terms)
+    cplx<T> q1 = {T(kS5a) * d1.x + T(kS5b) * d2.x, T(kS5a) * d1.y + T(kS5b) * d2.y};
+    cplx<T> q2 = {T(kS5b) * d1.x - T(kS5a) * d2.x, T(kS5b) * d1.y - T(kS5a) * d2.y};
+    v[S] = {p1.x + q1.y, p1.y - q1.x};
+    v[4 * S] = {p1.x - q1.y, p1.y + q1.x};
+    v[2 * S] = {p2.x + q2.y, p2.y - q2.x};
+    v[3 * S] = {p2.x - q2.y, p2.y + q2.x};
+  }
+};
+
+// Cooley-Tukey composite R = R1*R2 entirely in registers:
+//   n = R2*n1 + n2, k = k1 + R1*k2 :  X[k1 + R1 k2] = sum_n2 W_R2^{n2 k2} W_R^{n2 k1} (sum_n1 x[R2 n1 + n2] W_R1^{n1 k1})
+// Output is written back in natural order (needs a register permutation, free after unrolling).
+template <int R1, int R2, int S, class T>
+struct DftCT {
+  static constexpr int R = R1 * R2;
+  template <int N2, int K1> static ACC_HD void tw_row(cplx<T>* v) {
+    if constexpr (K1 < R1) {
+      v[(R2 * K1 + N2) * S] = mul_root<R, N2 * K1, T>(v[(R2 * K1 + N2) * S]);
+      tw_row<N2, K1 + 1>(v);
+    }
+  }
+  template <int N2> static ACC_HD void inner(cplx<T>* v) {
+    if constexpr (N2 < R2) {
+      // DFT_R1 over n1 of x[R2 n1 + n2]  (stride R2*S), result A[n2][k1] stored at position R2*k1 + n2
+      Dft<R1, R2 * S, T>::run(v + N2 * S);
+      tw_row<N2, 0>(v);
+      inner<N2 + 1>(v);
+    }
+  }
+  template <int K1> static ACC_HD void outer(cplx<T>* v) {
+    if constexpr (K1 < R1) {
+      // DFT_R2 over n2 of A[n2][k1] (positions R2*k1 + n2, stride S) -> X[k1 + R1 k2] left at R2*k1 + k2
+      Dft<R2, S, T>::run(v + R2 * K1 * S);
+      outer<K1 + 1>(v);
+    }
+  }
+  static ACC_HD void run(cplx<T>* v) {
+    inner<0>(v);
+    outer<0>(v);
+    // permute: position R2*k1 + k2 holds X[k1 + R1*k2]
+    cplx<T> tmp[R];
+    ACC_UNROLL
+    for (int k1 = 0; k1 < R1; ++k1)
+      ACC_UNROLL
+      for (int k2 = 0; k2 < R2; ++k2) tmp[k1 + R1 * k2] = v[(R2 * k1 + k2) * S];
+    ACC_UNROLL
+    for (int i = 0; i < R; ++i) v[i * S] = tmp[i];
+  }
+};
+template <int S, class T> struct Dft<6, S, T> : DftCT<3, 2, S, T> {};
+template <int S, class T> struct Dft<8, S, T> : DftCT<4, 2, S, T> {};
+template <int S, class T> struct Dft<12, S, T> : DftCT<3, 4, S, T> {};
+template <int S, class T> struct Dft<16, S, T> : DftCT<4, 4, S, T> {};
+
+// ---- schedule ------------------------------------------------------------------------------------
+template <int N_, int G_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
+struct Sched {
+  static constexpr int N = N_;
+  static constexpr int G = G_;   // threads per column
+  static constexpr int R[4] = {R0_, R1_, R2_, R3_};
+  static constexpr int NP = (R1_ == 1) ? 1 : (R2_ == 1) ? 2 : (R3_ == 1) ? 3 : 4;
+  static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
+  static constexpr int radix(int p) { return R[p]; }
+  static constexpr int ns(int p) { return p == 0 ? 1 : p == 1 ? R0_ : p == 2 ? R0_ * R1_ : R0_ * R1_ * R2_; }
+  static constexpr int nb(int p) { return N_ / R[p]; }
+  static constexpr int cnt(int p) { return (nb(p) + G_ - 1) / G_; }
+  static constexpr int regs(int p) { return cnt(p) * R[p]; }
+  static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+  static constexpr int NREG = cmax(cmax(regs(0), NP > 1 ? regs(1) : 0), cmax(NP > 2 ? regs(2) : 0, NP > 3 ? regs(3) : 0));
+  // shared-memory index padding: one extra slot every 8 (kills the stride-R conflicts of the
+  // early scatter passes for 16-byte and 8-byte elements alike)
+  static ACC_HD int phys(int i) { return i + (i >> 3); }
+  static constexpr int SMEM_ELEMS = N_ + (N_ >> 3) + 1;
+};
+
+// ---- per-pass building blocks ------------------------------------------------------------------------
+// tw: table W_M[k] = exp(-2 pi i k / M), k < M, with M = S::N * TWS  (TWS = 2 lets the r2c kernels share
+// the length-2M table they need for the split step).
+template <class S, int P, int TWS, class T>
+ACC_HD void pass_compute(cplx<T>* v, int t, const cplx<T>* __restrict__ tw) {
+  constexpr int R = S::radix(P), NS = S::ns(P), NB = S::nb(P), CNT = S::cnt(P);
+  constexpr int TSTEP = (S::N / (NS * R)) * TWS;
+  ACC_UNROLL
+  for (int u = 0; u < CNT; ++u) {
+    const int j = t + u * S::G;
+    if (CNT * S::G == NB || j < NB) {
+      if constexpr (NS > 1) {
+        const int q = (j % NS) * TSTEP;
+        ACC_UNROLL
+        for (int r = 1; r < R; ++r) v[u * R + r] = cmul(v[u * R + r], tw[r * q]);
+      }
+      Dft<R, 1, T>::run(v + u * R);
+    }
+  }
+}
+
+// scatter pass-P results into a column's shared-memory image; addr(i) maps logical index -> pointer
+template <class S, int P, class T, class Addr>
+ACC_HD void pass_scatter(const cplx<T>* v, int t, Addr addr) {
+  constexpr int R = S::radix(P), NS = S::ns(P), NB = S::nb(P), CNT = S::cnt(P);
+  ACC_UNROLL
+  for (int u = 0; u < CNT; ++u) {
+    const int j = t + u * S::G;
+    if (CNT * S::G == NB || j < NB) {
+      const int j0 = (j / NS) * NS * R + (j % NS);
+      ACC_UNROLL
+      for (int r = 0; r < R; ++r) *addr(j0 + r * NS) = v[u * R + r];
+    }
+  }
+}
+
+// gather pass-P operands:  v[u*R + r] = x[j + r*N/R]
+template <class S, int P, class T, class Addr>
+ACC_HD void pass_gather(cplx<T>* v, int t, Addr addr) {
+  constexpr int R = S::radix(P), NB = S::nb(P), CNT = S::cnt(P);
+  ACC_UNROLL
+  for (int u = 0; u < CNT; ++u) {
+    const int j = t + u * S::G;
+    if (CNT * S::G == NB || j < NB) {
+      ACC_UNROLL
+      for (int r = 0; r < R; ++r) v[u * R + r] = *addr(j + r * NB);
+    }
+  }
+}
+
+// visit the (logical index, register) pairs of pass P in gather order:  f(index, v[slot])
+template <class S, int P, class T, class F>
+ACC_HD void pass_foreach(cplx<T>* v, int t, F f) {
+  constexpr int R = S::radix(P), NB = S::nb(P), CNT = S::cnt(P);
+  ACC_UNROLL
+  for (int u = 0; u < CNT; ++u) {
+    const int j = t + u * S::G;
+    if (CNT * S::G == NB || j < NB) {
+      ACC_UNROLL
+      for (int r = 0; r < R; ++r) f(j + r * NB, v[u * R + r]);
+    }
+  }
+}
+
+// Run passes 0..NP-1 on registers already holding pass-0 operands (gather order); on return the
+// registers hold the final outputs in pass-(NP-1) gather order (index j + r*N/R_last).
+// smem_addr(i) -> pointer to this column's slot i;  sync() is a CTA-wide barrier.
+template <class S, int TWS, class T, class Addr, class Sync>
+ACC_HD void fft_passes(cplx<T>* v, int t, const cplx<T>* __restrict__ tw, Addr smem_addr, Sync sync) {
+  pass_compute<S, 0, TWS>(v, t, tw);
+  if constexpr (S::NP > 1) {
+    pass_scatter<S, 0>(v, t, smem_addr);
+    sync();
+    pass_gather<S, 1>(v, t, smem_addr);
+    pass_compute<S, 1, TWS>(v, t, tw);
+  }
+  if constexpr (S::NP > 2) {
+    sync();
+    pass_scatter<S, 1>(v, t, smem_addr);
+    sync();
+    pass_gather<S, 2>(v, t, smem_addr);
+    pass_compute<S, 2, TWS>(v, t, tw);
+  }
+  if constexpr (S::NP > 3) {
+    sync();
+    pass_scatter<S, 2>(v, t, smem_addr);
+    sync();
+    pass_gather<S, 3>(v, t, smem_addr);
+    pass_compute<S, 3, TWS>(v, t, tw);
+  }
+}
+
+}  // namespace accfft_b200

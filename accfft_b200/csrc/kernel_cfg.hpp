@@ -1,0 +1,33 @@
+// kernel_cfg.hpp -- CTA shapes derived from a schedule (shared by the CUDA backend and tests/emul).
+#pragma once
+#include "fft_engine.cuh"
+
+namespace accfft_b200 {
+
+#ifndef ACCFFT_MAX_STRIDED_THREADS
+#define ACCFFT_MAX_STRIDED_THREADS 512
+#endif
+#ifndef ACCFFT_MAX_STRIDED_SMEM
+#define ACCFFT_MAX_STRIDED_SMEM (100 * 1024)
+#endif
+
+template <class T, class S>
+struct Cfg {
+  // strided kernels: TC adjacent columns per tile; 128-byte row segments when threads / smem allow
+  static constexpr int tc_pick() {
+    int tc = 128 / (int)sizeof(cplx<T>);
+    while (tc > 1 && (S::G * tc > ACCFFT_MAX_STRIDED_THREADS ||
+                      (long long)S::SMEM_ELEMS * tc * (int)sizeof(cplx<T>) > ACCFFT_MAX_STRIDED_SMEM))
+      tc /= 2;
+    return tc;
+  }
+  static constexpr int TC = tc_pick();
+  static constexpr int STRIDED_THREADS = S::G * TC;
+  static constexpr int STRIDED_SMEM = S::SMEM_ELEMS * TC * (int)sizeof(cplx<T>);
+  // contiguous kernels: PC pencils per CTA, about 128 threads
+  static constexpr int PC = (S::G >= 128) ? 1 : 128 / S::G;
+  static constexpr int CONTIG_THREADS = S::G * PC;
+  static constexpr int CONTIG_SMEM = S::SMEM_ELEMS * PC * (int)sizeof(cplx<T>);
+};
+
+}  // namespace accfft_b200

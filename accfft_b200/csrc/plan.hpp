@@ -1,0 +1,78 @@
+// plan.hpp -- backend-agnostic plan: geometry -> per-stage descriptors -> launches.
+// Mirrors what accfft_plan_dft_3d_{r2c,c2c}_gpu builds (src/accfft_gpu.cpp:77-442, :704-931) and what
+// accfft_execute_gpu / accfft_execute_c2c_gpu run (:444-623, :943-1136), but every pencil transpose
+// is fused into the neighbouring FFT stage's stores (see stage.cuh) and the exchange buffers are the
+// peers' own stage buffers (NVLink peer stores), not a host-staged MPI_Alltoall.
+#pragma once
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include "decomp.hpp"
+#include "stage.cuh"
+
+namespace accfft_b200 {
+
+enum Kind : int { K_STRIDED_C2C = 0, K_CONTIG_C2C = 1, K_CONTIG_R2C = 2, K_CONTIG_C2R = 3, K_COPY = 4 };
+enum Prec : int { PREC_DOUBLE = 0, PREC_FLOAT = 1 };
+
+struct Launch {
+  Kind kind;
+  Prec prec;
+  int fftN;        // length of the complex engine transform (M = N/2 for r2c / c2r)
+  bool inverse;
+  StageDesc desc;
+};
+
+// Device services of ONE rank.  The product implements this with CUDA (backend_cuda.cu); tests/emul
+// implements it with host memory and a fiber emulator (test infrastructure only).
+struct Backend {
+  virtual ~Backend() {}
+  virtual bool supported(Kind kind, Prec prec, int fftN) = 0;
+  virtual const void* twiddle(Prec prec, int tableN) = 0;   // W_tableN[k], k < tableN
+  virtual int launch(const Launch& l) = 0;                   // enqueue on the plan's stream; 0 = ok
+  virtual int barrier() = 0;                                 // all ranks of the comm, stream ordered
+};
+
+struct Geometry {
+  int n[3];
+  int np[2], coords[2];
+  bool r2c;
+  int n2c;                 // N2/2+1 (r2c) or N2 (c2c)
+  Blk i0, i1;              // input block:  [i0.size][i1.size][N2]
+  Blk k2;                  // after exchange 1: [i0.size][N1][k2.size]
+  Blk k1;                  // after exchange 2: [N0][k1.size][k2.size]  (= output)
+  LocalSizes L;
+};
+
+Geometry make_geometry(const int n[3], const int np[2], const int coords[2], bool r2c, int sizeofReal);
+
+inline int rank_of(const int np[2], int c0, int c1) { return c0 * np[1] + c1; }
+
+struct Plan {
+  Geometry g;
+  Prec prec;
+  bool inplace;
+  Backend* be;
+  int nprocs;
+  // exchange buffers of every rank of the comm as seen from this rank (self = local pointers)
+  std::vector<void*> peerA, peerB;
+  std::string error;
+
+  // the three forward and three inverse stages; `in` / `out` are the user's buffers
+  Launch fwd_z(const void* in, bool in_padded) const;
+  Launch fwd_y() const;
+  Launch fwd_x(void* out) const;
+  Launch inv_x(const void* in) const;
+  Launch inv_y() const;
+  Launch inv_z(void* out, bool out_padded) const;
+
+  bool check_supported();
+  int execute_forward(const void* in, void* out, bool in_padded);
+  int execute_inverse(const void* in, void* out, bool out_padded);
+  // fused forward -> spectral symbol -> inverse (laplace / biharmonic; src/operators_gpu.txx:280-334, :555-609)
+  int execute_spectral(const void* in, void* out, int op);
+};
+
+unsigned blk_magic(int blk);
+
+}  // namespace accfft_b200

@@ -1,0 +1,277 @@
+// stage.cuh -- the per-axis stage kernels of the distributed 3-D transform (bodies only).
+//
+// One "stage" = batched 1-D transforms along one pencil axis, with the pencil transpose of the
+// reference fused into the kernel's stores: every output element is written straight to the rank
+// (peer-mapped buffer) that owns it in the NEXT stage's layout.  This replaces, per stage,
+//   cufftExec*                       (src/accfft_gpu.cpp:477-539, :541-602)
+// + pack kernel / memcpy_cuda        (src/transpose_cuda.cu:59-75, :97-204)
+// + cudaMemcpy D2H / MPI_Alltoall[v] / cudaMemcpy H2D   (src/transpose_gpu.cpp:3940-3955)
+// + unpack kernel                    (src/transpose_cuda.cu:13-21)
+// of the reference.  Bodies are __host__ __device__ templates over an execution context so the CPU
+// fiber emulator in tests/emul can execute the identical code (test infrastructure only).
+#pragma once
+#include "fft_engine.cuh"
+
+namespace accfft_b200 {
+
+constexpr int kMaxSeg = 16;   // max ranks in one row / column group
+
+// destination of output indices [s*blk, (s+1)*blk) of every column: the buffer of group peer s
+struct SegDst {
+  void* base;            // peer-mapped (or local) buffer, offset already folded in
+  long long strideA;     // elements per step of the column's outer index a
+  long long strideB;     // elements per step of the column's inner index b
+  long long strideI;     // elements per step of the transform index (k - s*blk)
+};
+
+enum SpectralOp : int {
+  OP_NONE = 0,
+  OP_SCALE = 1,       // multiply by scale
+  OP_GRAD = 2,        // i * k_axis * scale          (src/operators_cuda.cu:15-112)
+  OP_LAPLACE = 3,     // -(kx^2+ky^2+kz^2) * scale   (src/operators_cuda.cu:114-158)
+  OP_BIHARMONIC = 4,  // (kx^2+ky^2+kz^2)^2 * scale  (src/operators_cuda.cu:160-205)
+};
+
+struct StageDesc {
+  const void* in;
+  long long inStrideA, inStrideB, inStrideI;   // in elements of the input type
+  int nA, nB;                                  // columns are indexed (a, b), b fastest
+  int nseg, blk;
+  unsigned blkMagic;                           // ceil(2^32 / blk)
+  int pad0;
+  SegDst seg[kMaxSeg];
+  const void* tw;                              // W_M[k], see fft_engine.cuh
+  // spectral operator applied to the transform output (forward stages) -- see SpectralOp
+  int op;
+  int opAxis;            // OP_GRAD: which wave number (0,1,2) multiplies
+  int n[3];              // global grid
+  int kind[3];           // how to obtain the global frequency index along x,y,z for an output element:
+                         //   0 = transform index k, 1 = a + off, 2 = b + off, 3 = (b / div) + off, 4 = (b % div) + off
+  int off[3];
+  int div;
+  double scale;
+};
+
+ACC_HD int seg_of(const StageDesc& d, int k) {
+  if (d.nseg == 1) return 0;
+  if (d.blk == 1) return k;
+  return (int)(((unsigned long long)(unsigned)k * d.blkMagic) >> 32);
+}
+
+// wave number with the reference's Nyquist filter:  k = X > N/2 ? X-N : X;  k = 0 at X == N/2
+ACC_HD long long wave_number(int X, int N) {
+  long long w = X;
+  if (X > N / 2) w -= N;
+  if (X == N / 2) w = 0;
+  return w;
+}
+
+ACC_HD int freq_index(const StageDesc& d, int ax, int k, int a, int b) {
+  switch (d.kind[ax]) {
+    case 0: return k + d.off[ax];
+    case 1: return a + d.off[ax];
+    case 2: return b + d.off[ax];
+    case 3: return b / d.div + d.off[ax];
+    default: return b % d.div + d.off[ax];
+  }
+}
+
+template <class T>
+ACC_HD cplx<T> apply_op(const StageDesc& d, cplx<T> v, int k, int a, int b) {
+  if (d.op == OP_NONE) return v;
+  if (d.op == OP_SCALE) return {T(v.x * d.scale), T(v.y * d.scale)};
+  if (d.op == OP_GRAD) {
+    const int ax = d.opAxis;
+    const double w = d.scale * (double)wave_number(freq_index(d, ax, k, a, b), d.n[ax]);
+    return {T(-w * v.y), T(w * v.x)};
+  }
+  const long long wx = wave_number(freq_index(d, 0, k, a, b), d.n[0]);
+  const long long wy = wave_number(freq_index(d, 1, k, a, b), d.n[1]);
+  const long long wz = wave_number(freq_index(d, 2, k, a, b), d.n[2]);
+  const double s2 = (double)(wx * wx + wy * wy + wz * wz);
+  const double w = d.scale * (d.op == OP_LAPLACE ? -s2 : s2 * s2);
+  return {T(w * v.x), T(w * v.y)};
+}
+
+// ================================================================================================
+// strided c2c: transform index strided in memory, TC adjacent columns (unit stride) per CTA tile.
+// Used for the Y and X passes (reference: fplan_1 / fplan_2, src/accfft_gpu.cpp:208-253).
+// threads = S::G * TC;  tid -> (c = tid % TC, t = tid / TC);  smem layout [phys(i)][c]
+// ================================================================================================
+template <class T, class S, int TC, bool INV, class Ctx>
+ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
+  const int tid = ctx.tid();
+  const int c = tid % TC, t = tid / TC;
+  const int tpa = (d.nB + TC - 1) / TC;
+  const long long tile = ctx.bid();
+  const int a = (int)(tile / tpa);
+  const int b = (int)(tile % tpa) * TC + c;
+  const bool valid = b < d.nB;
+  cplx<T> v[S::NREG];
+  ACC_UNROLL
+  for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
+  if (valid) {
+    const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + b;
+    const long long si = d.inStrideI;
+    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) {
+      cplx<T> x = in[(long long)i * si];
+      r = INV ? cswap(x) : x;
+    });
+  }
+  cplx<T>* sm = (cplx<T>*)ctx.smem();
+  fft_passes<S, 1>(v, t, (const cplx<T>*)d.tw, [&](int i) { return sm + S::phys(i) * TC + c; },
+                   [&]() { ctx.sync(); });
+  if (valid) {
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) {
+      const int s = seg_of(d, k);
+      const SegDst& sd = d.seg[s];
+      cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB +
+                     (long long)(k - s * d.blk) * sd.strideI;
+      cplx<T> y = INV ? cswap(r) : r;
+      *dst = apply_op(d, y, k, a, b);
+    });
+  }
+}
+
+// ================================================================================================
+// contiguous c2c: transform index has unit stride; PC pencils per CTA, G threads per pencil.
+// Used for the Z pass of c2c plans (reference fplan_0 of the c2c plan, src/accfft_gpu.cpp:767-790).
+// ================================================================================================
+template <class T, class S, int PC, bool INV, class Ctx>
+ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
+  const int tid = ctx.tid();
+  const int t = tid % S::G, pcl = tid / S::G;
+  const long long idx = ctx.bid() * PC + pcl;
+  const bool valid = idx < (long long)d.nA * d.nB;
+  const int a = valid ? (int)(idx / d.nB) : 0;
+  const int b = valid ? (int)(idx % d.nB) : 0;
+  cplx<T> v[S::NREG];
+  ACC_UNROLL
+  for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
+  if (valid) {
+    const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB;
+    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) {
+      cplx<T> x = in[i];
+      r = INV ? cswap(x) : x;
+    });
+  }
+  cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
+  fft_passes<S, 1>(v, t, (const cplx<T>*)d.tw, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  if (valid) {
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) {
+      const int s = seg_of(d, k);
+      const SegDst& sd = d.seg[s];
+      cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB +
+                     (long long)(k - s * d.blk) * sd.strideI;
+      cplx<T> y = INV ? cswap(r) : r;
+      *dst = apply_op(d, y, k, a, b);
+    });
+  }
+}
+
+// ================================================================================================
+// contiguous r2c of even length N2 = 2*M: one M-point complex FFT on (x[2n], x[2n+1]) pairs plus the
+// split step  X[k] = E[k] + W_N2^k O[k].   Reference: fplan_0 = D2Z (src/accfft_gpu.cpp:173-189).
+// S is the schedule of the M-point transform; d.tw is the table of N2 = 2M entries.
+// Input strides are in units of REAL elements and must be even.
+// ================================================================================================
+template <class T, class S, int PC, class Ctx>
+ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
+  constexpr int M = S::N;
+  const int tid = ctx.tid();
+  const int t = tid % S::G, pcl = tid / S::G;
+  const long long idx = ctx.bid() * PC + pcl;
+  const bool valid = idx < (long long)d.nA * d.nB;
+  const int a = valid ? (int)(idx / d.nB) : 0;
+  const int b = valid ? (int)(idx % d.nB) : 0;
+  cplx<T> v[S::NREG];
+  ACC_UNROLL
+  for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
+  if (valid) {
+    const cplx<T>* in = (const cplx<T>*)((const T*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB);
+    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = in[i]; });
+  }
+  cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
+  const cplx<T>* tw = (const cplx<T>*)d.tw;
+  fft_passes<S, 2>(v, t, tw, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  // publish Z so every thread can read its mirror partner Z[M-k]
+  if constexpr (S::NP > 1) ctx.sync();
+  pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { sm[S::phys(k)] = r; });
+  ctx.sync();
+  if (valid) {
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& z) {
+      auto put = [&](int kk, cplx<T> y) {
+        const int s = seg_of(d, kk);
+        const SegDst& sd = d.seg[s];
+        cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB +
+                       (long long)(kk - s * d.blk) * sd.strideI;
+        *dst = apply_op(d, y, kk, a, b);
+      };
+      if (k == 0) {
+        put(0, cplx<T>{z.x + z.y, T(0)});
+        put(M, cplx<T>{z.x - z.y, T(0)});
+      } else {
+        const cplx<T> p = sm[S::phys(M - k)];
+        const cplx<T> w = tw[k];
+        const cplx<T> e = {z.x + p.x, z.y - p.y};      // Z[k] + conj(Z[M-k])
+        const cplx<T> o = {z.y + p.y, p.x - z.x};      // -i * (Z[k] - conj(Z[M-k]))
+        const cplx<T> wo = cmul(w, o);
+        put(k, cplx<T>{T(0.5) * (e.x + wo.x), T(0.5) * (e.y + wo.y)});
+      }
+    });
+  }
+}
+
+// ================================================================================================
+// contiguous c2r of even length N2 = 2*M (unnormalised, like cufftExecZ2D / fftw c2r):
+//   Z'[k] = (X[k] + conj(X[M-k])) + i conj(W_N2^k) (X[k] - conj(X[M-k])),  z = IDFT_M(Z'),  x[2n] + i x[2n+1] = z[n]
+// Imaginary parts of X[0] and X[M] are ignored, as FFTW / cuFFT do.   Reference: iplan_0 = Z2D
+// (src/accfft_gpu.cpp:191-206).  Output strides (seg[0]) are in units of REAL elements and must be even.
+// ================================================================================================
+template <class T, class S, int PC, class Ctx>
+ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
+  constexpr int M = S::N;
+  const int tid = ctx.tid();
+  const int t = tid % S::G, pcl = tid / S::G;
+  const long long idx = ctx.bid() * PC + pcl;
+  const bool valid = idx < (long long)d.nA * d.nB;
+  const int a = valid ? (int)(idx / d.nB) : 0;
+  const int b = valid ? (int)(idx % d.nB) : 0;
+  cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
+  const cplx<T>* tw = (const cplx<T>*)d.tw;
+  if (valid) {
+    const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB;
+    for (int i = t; i <= M; i += S::G) sm[S::phys(i)] = apply_op(d, in[i], i, a, b);
+  } else {
+    for (int i = t; i <= M; i += S::G) sm[S::phys(i)] = {T(0), T(0)};
+  }
+  ctx.sync();
+  cplx<T> v[S::NREG];
+  ACC_UNROLL
+  for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
+  pass_foreach<S, 0>(v, t, [&](int k, cplx<T>& r) {
+    const cplx<T> A = sm[S::phys(k)];
+    const cplx<T> B = sm[S::phys(M - k)];
+    cplx<T> z;
+    if (k == 0) {
+      z = {A.x + B.x, A.x - B.x};
+    } else {
+      const cplx<T> w = tw[k];
+      const cplx<T> e = {A.x + B.x, A.y - B.y};   // X[k] + conj(X[M-k])
+      const cplx<T> D = {A.x - B.x, A.y + B.y};   // X[k] - conj(X[M-k])
+      // i * conj(w) * D
+      const cplx<T> q = {-(w.x * D.y - w.y * D.x), w.x * D.x + w.y * D.y};
+      z = cadd(e, q);
+    }
+    r = cswap(z);   // inverse transform = swap . forward . swap
+  });
+  ctx.sync();
+  fft_passes<S, 2>(v, t, tw, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  if (valid) {
+    const SegDst& sd = d.seg[0];
+    cplx<T>* out = (cplx<T>*)((T*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB);
+    pass_foreach<S, S::NP - 1>(v, t, [&](int nidx, cplx<T>& r) { out[nidx] = cswap(r); });
+  }
+}
+
+}  // namespace accfft_b200

@@ -1,0 +1,295 @@
+// emul.cpp -- TEST INFRASTRUCTURE ONLY.  A CPU emulator for the stage kernels of accfft_b200.
+//
+// The kernel bodies in accfft_b200/csrc/stage.cuh are __host__ __device__ templates over an execution
+// context.  Here each CUDA thread of a CTA runs as a ucontext fiber (__syncthreads == yield to a
+// round-robin scheduler), each rank of the process grid runs as an OS thread, and the inter-rank
+// barrier is a pthread barrier.  The plan / descriptor code (plan.cpp) is the very same code the CUDA
+// backend uses, so index math, uneven splits and peer addressing are validated without a GPU.
+// Nothing in the product links against this file; libaccfft_b200.so has no CPU execution path.
+#include <pthread.h>
+#include <string.h>
+#include <ucontext.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <map>
+#include <thread>
+#include <vector>
+
+#include "../../accfft_b200/csrc/kernel_cfg.hpp"
+#include "../../accfft_b200/csrc/plan.hpp"
+
+using namespace accfft_b200;
+
+// ---------------------------------------------------------------------------------------------------
+// fiber CTA
+// ---------------------------------------------------------------------------------------------------
+struct CtaEmu {
+  int nthreads = 0;
+  std::vector<ucontext_t> ctx;
+  std::vector<char*> stacks;
+  std::vector<char> done;
+  ucontext_t sched;
+  int cur = 0;
+  std::function<void(int)> body;
+  static constexpr size_t kStack = 256 * 1024;
+  ~CtaEmu() {
+    for (char* s : stacks) free(s);
+  }
+};
+static thread_local CtaEmu* g_cta = nullptr;
+
+static void fiber_tramp() {
+  CtaEmu* c = g_cta;
+  const int tid = c->cur;
+  c->body(tid);
+  c->done[tid] = 1;
+  swapcontext(&c->ctx[tid], &c->sched);
+}
+static void fiber_sync() {
+  CtaEmu* c = g_cta;
+  const int tid = c->cur;
+  swapcontext(&c->ctx[tid], &c->sched);
+}
+static void run_cta(CtaEmu& c, int nthreads, std::function<void(int)> body) {
+  g_cta = &c;
+  c.body = body;
+  if ((int)c.stacks.size() < nthreads) {
+    for (int i = (int)c.stacks.size(); i < nthreads; ++i) c.stacks.push_back((char*)malloc(CtaEmu::kStack));
+  }
+  c.ctx.resize(nthreads);
+  c.done.assign(nthreads, 0);
+  c.nthreads = nthreads;
+  for (int i = 0; i < nthreads; ++i) {
+    getcontext(&c.ctx[i]);
+    c.ctx[i].uc_stack.ss_sp = c.stacks[i];
+    c.ctx[i].uc_stack.ss_size = CtaEmu::kStack;
+    c.ctx[i].uc_link = &c.sched;
+    makecontext(&c.ctx[i], fiber_tramp, 0);
+  }
+  bool alive = true;
+  while (alive) {
+    alive = false;
+    for (int i = 0; i < nthreads; ++i) {
+      if (c.done[i]) continue;
+      c.cur = i;
+      swapcontext(&c.sched, &c.ctx[i]);
+      if (!c.done[i]) alive = true;
+    }
+  }
+}
+
+struct EmuCtx {
+  int tid_;
+  long long bid_;
+  void* smem_;
+  int tid() const { return tid_; }
+  long long bid() const { return bid_; }
+  void* smem() const { return smem_; }
+  void sync() const { fiber_sync(); }
+};
+
+template <class Body>
+static void run_grid(long long nblocks, int nthreads, size_t smem_bytes, Body body) {
+  CtaEmu cta;
+  std::vector<char> smem(smem_bytes + 64);
+  for (long long b = 0; b < nblocks; ++b) {
+    memset(smem.data(), 0xCD, smem.size());
+    run_cta(cta, nthreads, [&](int tid) {
+      EmuCtx ctx{tid, b, (void*)smem.data()};
+      body(ctx);
+    });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dispatch (same schedule table as the CUDA backend)
+// ---------------------------------------------------------------------------------------------------
+template <class T, class S>
+static void emu_launch_sched(const Launch& l) {
+  using C = Cfg<T, S>;
+  const StageDesc& d = l.desc;
+  switch (l.kind) {
+    case K_STRIDED_C2C: {
+      const long long nb = (long long)d.nA * ((d.nB + C::TC - 1) / C::TC);
+      if (l.inverse)
+        run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) { strided_c2c_body<T, S, C::TC, true>(d, c); });
+      else
+        run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) { strided_c2c_body<T, S, C::TC, false>(d, c); });
+      break;
+    }
+    case K_CONTIG_C2C: {
+      const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
+      if (l.inverse)
+        run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2c_body<T, S, C::PC, true>(d, c); });
+      else
+        run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2c_body<T, S, C::PC, false>(d, c); });
+      break;
+    }
+    case K_CONTIG_R2C: {
+      const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
+      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_r2c_body<T, S, C::PC>(d, c); });
+      break;
+    }
+    case K_CONTIG_C2R: {
+      const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
+      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2r_body<T, S, C::PC>(d, c); });
+      break;
+    }
+    default:
+      fprintf(stderr, "emul: unsupported kind %d\n", (int)l.kind);
+      abort();
+  }
+}
+
+static bool emu_supported(int N) {
+#define X(N_, G_, R0, R1, R2, R3) \
+  if (N == N_) return true;
+#include "../../accfft_b200/csrc/schedules.def"
+#undef X
+  return false;
+}
+
+static void emu_launch(const Launch& l) {
+#define X(N_, G_, R0, R1, R2, R3)                                                       \
+  if (l.fftN == N_) {                                                                   \
+    if (l.prec == PREC_DOUBLE) emu_launch_sched<double, Sched<N_, G_, R0, R1, R2, R3>>(l); \
+    else emu_launch_sched<float, Sched<N_, G_, R0, R1, R2, R3>>(l);                        \
+    return;                                                                             \
+  }
+#include "../../accfft_b200/csrc/schedules.def"
+#undef X
+  fprintf(stderr, "emul: no schedule for N=%d\n", l.fftN);
+  abort();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backend + world
+// ---------------------------------------------------------------------------------------------------
+struct EmuWorld;
+struct EmuBackend : Backend {
+  EmuWorld* w;
+  std::map<std::pair<int, int>, std::vector<char>> tables;
+  bool supported(Kind, Prec, int fftN) override { return emu_supported(fftN); }
+  const void* twiddle(Prec prec, int M) override {
+    auto key = std::make_pair((int)prec, M);
+    auto it = tables.find(key);
+    if (it != tables.end()) return it->second.data();
+    std::vector<char> buf((size_t)M * (prec == PREC_DOUBLE ? 16 : 8));
+    for (int k = 0; k < M; ++k) {
+      const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)M;
+      if (prec == PREC_DOUBLE) {
+        ((double*)buf.data())[2 * k] = (double)cosl(ang);
+        ((double*)buf.data())[2 * k + 1] = (double)sinl(ang);
+      } else {
+        ((float*)buf.data())[2 * k] = (float)cosl(ang);
+        ((float*)buf.data())[2 * k + 1] = (float)sinl(ang);
+      }
+    }
+    auto& ref = tables[key] = std::move(buf);
+    return ref.data();
+  }
+  int launch(const Launch& l) override {
+    emu_launch(l);
+    return 0;
+  }
+  int barrier() override;
+};
+
+struct EmuWorld {
+  int n[3], np[2], nprocs;
+  bool r2c;
+  Prec prec;
+  std::vector<EmuBackend> be;
+  std::vector<Plan> plans;
+  std::vector<std::vector<char>> bufA, bufB;
+  pthread_barrier_t bar;
+};
+int EmuBackend::barrier() {
+  pthread_barrier_wait(&w->bar);
+  return 0;
+}
+
+extern "C" {
+
+void* emu_world_create(const int* n, int P0, int P1, int r2c, int prec) {
+  EmuWorld* w = new EmuWorld();
+  for (int i = 0; i < 3; ++i) w->n[i] = n[i];
+  w->np[0] = P0;
+  w->np[1] = P1;
+  w->nprocs = P0 * P1;
+  w->r2c = r2c != 0;
+  w->prec = (Prec)prec;
+  w->be.resize(w->nprocs);
+  w->plans.resize(w->nprocs);
+  w->bufA.resize(w->nprocs);
+  w->bufB.resize(w->nprocs);
+  pthread_barrier_init(&w->bar, nullptr, w->nprocs);
+  const int sz = prec == PREC_DOUBLE ? 8 : 4;
+  for (int r = 0; r < w->nprocs; ++r) {
+    int coords[2] = {r / P1, r % P1};
+    w->be[r].w = w;
+    Plan& p = w->plans[r];
+    p.g = make_geometry(w->n, w->np, coords, w->r2c, sz);
+    p.prec = w->prec;
+    p.inplace = false;
+    p.be = &w->be[r];
+    p.nprocs = w->nprocs;
+    // +64 bytes so that out-of-range writes are more likely to be caught by the canary check below
+    w->bufA[r].assign((size_t)p.g.L.alloc_max + 64, (char)0xEE);
+    w->bufB[r].assign((size_t)p.g.L.alloc_max + 64, (char)0xEE);
+  }
+  for (int r = 0; r < w->nprocs; ++r) {
+    Plan& p = w->plans[r];
+    for (int q = 0; q < w->nprocs; ++q) {
+      p.peerA.push_back(w->bufA[q].data());
+      p.peerB.push_back(w->bufB[q].data());
+    }
+    if (!p.check_supported()) {
+      fprintf(stderr, "emul: %s\n", p.error.c_str());
+      delete w;
+      return nullptr;
+    }
+  }
+  return w;
+}
+
+void emu_world_destroy(void* h) {
+  EmuWorld* w = (EmuWorld*)h;
+  pthread_barrier_destroy(&w->bar);
+  delete w;
+}
+
+long long emu_alloc_max(void* h, int rank) { return ((EmuWorld*)h)->plans[rank].g.L.alloc_max; }
+
+static int canaries_ok(EmuWorld* w) {
+  for (int r = 0; r < w->nprocs; ++r)
+    for (int i = 0; i < 64; ++i) {
+      if ((unsigned char)w->bufA[r][w->bufA[r].size() - 64 + i] != 0xEE) return 0;
+      if ((unsigned char)w->bufB[r][w->bufB[r].size() - 64 + i] != 0xEE) return 0;
+    }
+  return 1;
+}
+
+// mode: 0 forward, 1 inverse, 2 laplace, 3 biharmonic.  in/out: per-rank host pointers.
+int emu_execute(void* h, int mode, void** in, void** out, int padded) {
+  EmuWorld* w = (EmuWorld*)h;
+  std::vector<std::thread> th;
+  std::vector<int> rc(w->nprocs, 0);
+  for (int r = 0; r < w->nprocs; ++r) {
+    th.emplace_back([&, r]() {
+      Plan& p = w->plans[r];
+      if (mode == 0) rc[r] = p.execute_forward(in[r], out[r], padded != 0);
+      else if (mode == 1) rc[r] = p.execute_inverse(in[r], out[r], padded != 0);
+      else if (mode == 2) rc[r] = p.execute_spectral(in[r], out[r], OP_LAPLACE);
+      else rc[r] = p.execute_spectral(in[r], out[r], OP_BIHARMONIC);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w->nprocs; ++r)
+    if (rc[r]) return rc[r];
+  return canaries_ok(w) ? 0 : -99;
+}
+
+}  // extern "C"

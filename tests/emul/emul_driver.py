@@ -1,0 +1,172 @@
+"""ctypes driver for tests/emul/_build/libemul.so (CPU emulator of the stage kernels; test infra only)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "_build", "libemul.so")
+SOURCES = [os.path.join(HERE, "emul.cpp"), os.path.join(ROOT, "accfft_b200", "csrc", "plan.cpp")]
+HEADERS = [os.path.join(ROOT, "accfft_b200", "csrc", f)
+           for f in ("fft_engine.cuh", "stage.cuh", "plan.hpp", "decomp.hpp", "kernel_cfg.hpp", "schedules.def")]
+
+sys.path.insert(0, ROOT)
+from oracle import accfft_oracle as orc  # noqa: E402
+
+
+def build(force=False):
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    if not force and os.path.exists(LIB):
+        m = os.path.getmtime(LIB)
+        if all(os.path.getmtime(p) <= m for p in SOURCES + HEADERS):
+            return LIB
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unused-function", *SOURCES, "-o", LIB,
+           "-lpthread"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.emu_world_create.restype = ctypes.c_void_p
+        _lib.emu_world_create.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int]
+        _lib.emu_world_destroy.argtypes = [ctypes.c_void_p]
+        _lib.emu_alloc_max.restype = ctypes.c_longlong
+        _lib.emu_alloc_max.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _lib.emu_execute.restype = ctypes.c_int
+        _lib.emu_execute.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                     ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
+    return _lib
+
+
+class World:
+    """All ranks of a P0 x P1 grid in one process."""
+
+    def __init__(self, n, np_, r2c=True, single=False):
+        self.n, self.np_, self.r2c, self.single = tuple(n), tuple(np_), r2c, single
+        arr = (ctypes.c_int * 3)(*n)
+        self.h = lib().emu_world_create(arr, np_[0], np_[1], int(r2c), int(single))
+        if not self.h:
+            raise RuntimeError("emu_world_create failed (unsupported size?)")
+        self.nprocs = np_[0] * np_[1]
+        self.rdt = np.float32 if single else np.float64
+        self.cdt = np.complex64 if single else np.complex128
+
+    def close(self):
+        if self.h:
+            lib().emu_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def coords(self, r):
+        return orc.rank_to_coords(r, self.np_)
+
+    def _run(self, mode, ins, outs, padded=False):
+        pin = (ctypes.c_void_p * self.nprocs)(*[a.ctypes.data for a in ins])
+        pout = (ctypes.c_void_p * self.nprocs)(*[a.ctypes.data for a in outs])
+        rc = lib().emu_execute(self.h, mode, pin, pout, int(padded))
+        if rc:
+            raise RuntimeError(f"emu_execute rc={rc}")
+
+    def alloc_out(self):
+        """per-rank output buffers of alloc_max bytes"""
+        return [np.zeros(lib().emu_alloc_max(self.h, r) // self.rdt().itemsize, dtype=self.rdt)
+                for r in range(self.nprocs)]
+
+    def forward(self, x_global, padded=False):
+        n = self.n
+        ins = []
+        for r in range(self.nprocs):
+            loc = orc.local_input(x_global, n, self.np_, self.coords(r))
+            if self.r2c:
+                loc = loc.astype(self.rdt)
+                if padded:
+                    n2c = n[2] // 2 + 1
+                    buf = np.zeros(loc.shape[:2] + (2 * n2c,), dtype=self.rdt)
+                    buf[:, :, :n[2]] = loc
+                    loc = buf
+            else:
+                loc = loc.astype(self.cdt)
+            ins.append(np.ascontiguousarray(loc))
+        outs = self.alloc_out()
+        self._run(0, ins, outs, padded)
+        blocks = []
+        n2c = n[2] // 2 + 1 if self.r2c else n[2]
+        for r in range(self.nprocs):
+            c = self.coords(r)
+            s1 = orc.block(n[1], self.np_[0], c[0])[0]
+            s2 = orc.block(n2c, self.np_[1], c[1])[0]
+            cnt = n[0] * s1 * s2
+            blocks.append(outs[r].view(self.cdt)[:cnt].reshape(n[0], s1, s2).copy())
+        return blocks
+
+    def inverse(self, X_global, padded=False):
+        n = self.n
+        ins = []
+        for r in range(self.nprocs):
+            loc = orc.local_output(X_global, n, self.np_, self.coords(r), r2c=self.r2c).astype(self.cdt)
+            ins.append(np.ascontiguousarray(loc))
+        outs = self.alloc_out()
+        self._run(1, ins, outs, padded)
+        blocks = []
+        for r in range(self.nprocs):
+            c = self.coords(r)
+            s0 = orc.block(n[0], self.np_[0], c[0])[0]
+            s1 = orc.block(n[1], self.np_[1], c[1])[0]
+            if self.r2c:
+                row = 2 * (n[2] // 2 + 1) if padded else n[2]
+                blocks.append(outs[r][:s0 * s1 * row].reshape(s0, s1, row)[:, :, :n[2]].copy())
+            else:
+                blocks.append(outs[r].view(self.cdt)[:s0 * s1 * n[2]].reshape(s0, s1, n[2]).copy())
+        return blocks
+
+    def spectral(self, x_global, op):
+        n = self.n
+        ins = [np.ascontiguousarray(orc.local_input(x_global, n, self.np_, self.coords(r)).astype(self.rdt))
+               for r in range(self.nprocs)]
+        outs = self.alloc_out()
+        self._run({"laplace": 2, "biharmonic": 3}[op], ins, outs)
+        blocks = []
+        for r in range(self.nprocs):
+            c = self.coords(r)
+            s0 = orc.block(n[0], self.np_[0], c[0])[0]
+            s1 = orc.block(n[1], self.np_[1], c[1])[0]
+            blocks.append(outs[r][:s0 * s1 * n[2]].reshape(s0, s1, n[2]).copy())
+        return blocks
+
+
+if __name__ == "__main__":
+    cases = [((8, 8, 8), (1, 1)), ((16, 8, 12), (1, 1)), ((8, 8, 8), (1, 2)), ((8, 8, 8), (2, 2)),
+             ((12, 10, 16), (2, 4)), ((6, 12, 10), (3, 2)), ((5, 6, 6), (4, 2)), ((16, 12, 6), (2, 4)),
+             ((3, 5, 4), (4, 4)), ((32, 24, 20), (2, 2)), ((64, 48, 40), (1, 2))]
+    for n, np_ in cases:
+        x = orc.synthetic_real(n, 7)
+        w = World(n, np_, r2c=True)
+        X = orc.forward_r2c(x)
+        e1 = orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), X)
+        e1p = orc.rel_l2(orc.assemble_output(w.forward(x, padded=True), n, np_), X)
+        xb = orc.assemble_input(w.inverse(X), n, np_)
+        e2 = orc.rel_l2(xb, x * x.size)
+        lap = orc.rel_l2(orc.assemble_input(w.spectral(x, "laplace"), n, np_), orc.laplace(x))
+        w.close()
+        z = orc.synthetic_complex(n, 8)
+        w = World(n, np_, r2c=False)
+        Z = orc.forward_c2c(z)
+        e3 = orc.rel_l2(orc.assemble_output(w.forward(z), n, np_, r2c=False), Z)
+        zb = orc.assemble_input(w.inverse(Z), n, np_)
+        e4 = orc.rel_l2(zb, z * z.size)
+        w.close()
+        print(n, np_, "r2c %.2e (padded %.2e) c2r %.2e lap %.2e | c2c fwd %.2e inv %.2e" % (e1, e1p, e2, lap, e3, e4))
