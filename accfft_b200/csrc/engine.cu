@@ -1,0 +1,572 @@
+// engine.cu -- CUDA backend of the plan (twiddle tables, stage launches, inter-GPU barrier) and the
+// C ABI of libaccfft_b200.so (include/accfft_b200.h).
+//
+// Replaces, in the reference: Mem_Mgr_gpu / T_Plan_gpu (src/transpose_gpu.cpp:58-384), the cuFFT plan
+// set-up of accfft_plan_dft_3d_{r2c,c2c}_gpu (src/accfft_gpu.cpp:77-442, :704-931), the execute drivers
+// (:444-675, :943-1136) and the operator drivers (src/operators_gpu.txx:72-609).
+// There is no CPU path in this library: every entry point that computes launches sm_100a kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/accfft_b200.h"
+#include "plan.hpp"
+
+namespace accfft_b200 {
+
+// per-(kind, precision) launchers, one translation unit each (k_tu.cu)
+int accfft_launch_k0_p0(const Launch&, cudaStream_t);
+int accfft_launch_k1_p0(const Launch&, cudaStream_t);
+int accfft_launch_k2_p0(const Launch&, cudaStream_t);
+int accfft_launch_k3_p0(const Launch&, cudaStream_t);
+int accfft_launch_k0_p1(const Launch&, cudaStream_t);
+int accfft_launch_k1_p1(const Launch&, cudaStream_t);
+int accfft_launch_k2_p1(const Launch&, cudaStream_t);
+int accfft_launch_k3_p1(const Launch&, cudaStream_t);
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+#define CU(call)                                      \
+  do {                                                \
+    cudaError_t e__ = (call);                         \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+static bool length_supported(int N) {
+#define X(N_, G_, R0, R1, R2, R3) \
+  if (N == N_) return true;
+#include "schedules.def"
+#undef X
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inter-GPU barrier: every rank owns a flag array (one 64-bit epoch slot per peer) inside its exchange
+// slab; rank r arrives by storing the epoch into slot r of every peer and waits until all of its own
+// slots reached the epoch.  Stage kernels of the same stream have completed before the barrier kernel
+// starts, so their NVLink stores are performed; the system-scope fences order them with the flags.
+// ---------------------------------------------------------------------------------------------------
+struct BarrierDesc {
+  unsigned long long* flags[ACCFFTB_MAX_GROUP * ACCFFTB_MAX_GROUP];   // flag array of every rank (peer mapped)
+  int rank, nprocs;
+  unsigned long long epoch;
+  long long timeout_cycles;
+  int* status;   // device word, set to 1 on timeout
+};
+
+__global__ void k_barrier(const __grid_constant__ BarrierDesc b) {
+  const int q = (int)threadIdx.x;
+  if (q >= b.nprocs) return;
+  __threadfence_system();
+  unsigned long long* remote = b.flags[q] + b.rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(b.epoch) : "memory");
+  const unsigned long long* mine = b.flags[b.rank] + q;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= b.epoch) break;
+    if (clock64() - t0 > b.timeout_cycles) {
+      *b.status = 1;
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct Engine;
+struct CudaBackend : Backend {
+  Engine* e = nullptr;
+  bool supported(Kind, Prec, int fftN) override { return length_supported(fftN); }
+  const void* twiddle(Prec prec, int tableN) override;
+  int launch(const Launch& l) override;
+  int barrier() override;
+};
+
+constexpr size_t kFlagBytes = 4096;
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Engine {
+  Plan plan;
+  CudaBackend be;
+  int device = 0;
+  int rank = 0;
+  cudaStream_t stream = 0;
+  bool blocking = true;
+  bool wired = false;          // peers attached (always true for single-rank plans)
+  char* slab = nullptr;        // [A | B | flags] of this rank
+  size_t slab_bytes = 0, bufsz = 0;
+  void* spec = nullptr;        // lazily allocated spectrum scratch for grad / divergence
+  int* status_d = nullptr;     // barrier timeout word
+  std::vector<void*> opened;   // cudaIpcOpenMemHandle mappings to close
+  std::vector<unsigned long long*> flag_ptrs;
+  unsigned long long epoch = 0;
+  long long launches = 0;
+  std::map<std::pair<int, int>, void*> tables;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  // timing of the current call
+  bool timing = false;
+  double t_fft = 0, t_bar = 0;
+};
+
+const void* CudaBackend::twiddle(Prec prec, int M) {
+  auto key = std::make_pair((int)prec, M);
+  auto it = e->tables.find(key);
+  if (it != e->tables.end()) return it->second;
+  const size_t es = prec == PREC_DOUBLE ? 16 : 8;
+  std::vector<char> buf((size_t)M * es);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int k = 0; k < M; ++k) {
+    // exact octant symmetry is not needed for the 1e-12 bound; long double cosl/sinl round correctly enough
+    const long double ang = -two_pi * (long double)k / (long double)M;
+    if (prec == PREC_DOUBLE) {
+      ((double*)buf.data())[2 * k] = (double)cosl(ang);
+      ((double*)buf.data())[2 * k + 1] = (double)sinl(ang);
+    } else {
+      ((float*)buf.data())[2 * k] = (float)cosl(ang);
+      ((float*)buf.data())[2 * k + 1] = (float)sinl(ang);
+    }
+  }
+  void* d = nullptr;
+  if (cudaMalloc(&d, buf.size()) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, buf.data(), buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  e->tables[key] = d;
+  return d;
+}
+
+struct ScopedTimer {
+  Engine* e;
+  double* acc;
+  ScopedTimer(Engine* e_, double* acc_) : e(e_), acc(acc_) {
+    if (e->timing) cudaEventRecord(e->ev[0], e->stream);
+  }
+  ~ScopedTimer() {
+    if (e->timing) {
+      cudaEventRecord(e->ev[1], e->stream);
+      cudaEventSynchronize(e->ev[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+      *acc += 1e-3 * (double)ms;
+    }
+  }
+};
+
+int CudaBackend::launch(const Launch& l) {
+  if (!l.desc.tw) return fail(ACCFFTB_ERR_STATE, "twiddle table allocation failed");
+  ScopedTimer tm(e, &e->t_fft);
+  int rc = -1;
+  const int sel = (int)l.kind * 2 + (int)l.prec;
+  switch (sel) {
+    case 0: rc = accfft_launch_k0_p0(l, e->stream); break;
+    case 1: rc = accfft_launch_k0_p1(l, e->stream); break;
+    case 2: rc = accfft_launch_k1_p0(l, e->stream); break;
+    case 3: rc = accfft_launch_k1_p1(l, e->stream); break;
+    case 4: rc = accfft_launch_k2_p0(l, e->stream); break;
+    case 5: rc = accfft_launch_k2_p1(l, e->stream); break;
+    case 6: rc = accfft_launch_k3_p0(l, e->stream); break;
+    case 7: rc = accfft_launch_k3_p1(l, e->stream); break;
+    default: break;
+  }
+  if (rc == -1) return fail(ACCFFTB_ERR_UNSUPPORTED, "no kernel schedule for length " + std::to_string(l.fftN));
+  if (rc != 0) return cuda_fail((cudaError_t)rc, "stage kernel launch");
+  e->launches++;
+  return 0;
+}
+
+int CudaBackend::barrier() {
+  if (!e->wired) return fail(ACCFFTB_ERR_STATE, "multi-rank plan used before its peers were attached");
+  ScopedTimer tm(e, &e->t_bar);
+  BarrierDesc b;
+  memset(&b, 0, sizeof(b));
+  for (int q = 0; q < e->plan.nprocs; ++q) b.flags[q] = e->flag_ptrs[q];
+  b.rank = e->rank;
+  b.nprocs = e->plan.nprocs;
+  b.epoch = ++e->epoch;
+  b.timeout_cycles = 20LL * 1000 * 1000 * 1000;   // ~10 s at 2 GHz: a peer died or diverged
+  b.status = e->status_d;
+  k_barrier<<<1, 256, 0, e->stream>>>(b);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return cuda_fail(err, "barrier kernel launch");
+  e->launches++;
+  return 0;
+}
+
+static int engine_finish(Engine* e, int rc) {
+  if (rc) return rc;
+  if (e->blocking) {
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->plan.nprocs > 1) {
+      int st = 0;
+      CU(cudaMemcpy(&st, e->status_d, sizeof(int), cudaMemcpyDeviceToHost));
+      if (st) return fail(ACCFFTB_ERR_TIMEOUT, "inter-GPU barrier timed out");
+    }
+  }
+  return 0;
+}
+
+static void engine_free(Engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (void* p : e->opened) cudaIpcCloseMemHandle(p);
+  for (auto& kv : e->tables) cudaFree(kv.second);
+  if (e->slab) cudaFree(e->slab);
+  if (e->spec) cudaFree(e->spec);
+  if (e->status_d) cudaFree(e->status_d);
+  if (e->ev[0]) cudaEventDestroy(e->ev[0]);
+  if (e->ev[1]) cudaEventDestroy(e->ev[1]);
+}
+
+static void wire_self(Engine* e) {
+  const int np = e->plan.nprocs;
+  e->plan.peerA.assign(np, nullptr);
+  e->plan.peerB.assign(np, nullptr);
+  e->flag_ptrs.assign(np, nullptr);
+  e->plan.peerA[e->rank] = e->slab;
+  e->plan.peerB[e->rank] = e->slab + e->bufsz;
+  e->flag_ptrs[e->rank] = (unsigned long long*)(e->slab + 2 * e->bufsz);
+}
+
+// size of rank q's exchange buffers (its alloc_max, 256-byte aligned) -- every rank can compute it
+static size_t bufsz_of(const Engine* e, int q) {
+  int coords[2] = {q / e->plan.g.np[1], q % e->plan.g.np[1]};
+  const int sz = e->plan.prec == PREC_DOUBLE ? 8 : 4;
+  LocalSizes L = e->plan.g.r2c ? local_size_r2c(e->plan.g.n, e->plan.g.np, coords, sz)
+                               : local_size_c2c(e->plan.g.n, e->plan.g.np, coords, sz);
+  return align_up((size_t)std::max<long long>(L.alloc_max, 16), 256);
+}
+
+struct IpcBlob {
+  cudaIpcMemHandle_t handle;   // 64 bytes
+  unsigned long long slab_bytes;
+  int rank, nprocs;
+  unsigned magic;
+  char pad[ACCFFTB_IPC_BLOB_BYTES - 64 - 8 - 12];
+};
+static_assert(sizeof(IpcBlob) == ACCFFTB_IPC_BLOB_BYTES, "blob size");
+
+struct TimerScope {
+  Engine* e;
+  double* timer;
+  int nslots;
+  TimerScope(Engine* e_, double* timer_, int nslots_) : e(e_), timer(timer_), nslots(nslots_) {
+    e->timing = timer != nullptr;
+    e->t_fft = e->t_bar = 0;
+  }
+  ~TimerScope() {
+    if (timer) {
+      timer[0] += e->t_bar;
+      timer[2] += e->t_bar;
+      timer[4] += e->t_fft;
+    }
+    e->timing = false;
+  }
+};
+
+}  // namespace accfft_b200
+
+using namespace accfft_b200;
+
+struct accfftb_plan {
+  Engine e;
+};
+
+static bool overflow_guard(const LocalSizes& L, int sizeof_real) {
+  // the reference refuses local blocks of more than 2^31 elements (src/accfft_common.cpp:179-184)
+  return L.alloc_max / sizeof_real > (1LL << 31);
+}
+
+extern "C" {
+
+const char* accfftb_last_error(void) { return g_err.c_str(); }
+const char* accfftb_version(void) { return "accfft_b200 0.1 (sm_100a)"; }
+
+int accfftb_create_comm_dims(int nprocs, int c_dims[2]) {
+  if (nprocs > 0 && c_dims[0] * c_dims[1] == nprocs && c_dims[0] > 0) return 0;
+  dims_create(nprocs, c_dims);
+  return 1;
+}
+
+void accfftb_rank_to_coords(int rank, const int c_dims[2], int coords[2]) {
+  coords[0] = rank / c_dims[1];
+  coords[1] = rank % c_dims[1];
+}
+
+static void copy3(int* dst, const int* src) {
+  if (dst)
+    for (int i = 0; i < 3; ++i) dst[i] = src[i];
+}
+
+long long accfftb_local_size_dft_r2c(const int n[3], const int c_dims[2], const int coords[2], int sizeof_real,
+                                     int isize[3], int istart[3], int osize[3], int ostart[3]) {
+  LocalSizes L = local_size_r2c(n, c_dims, coords, sizeof_real);
+  copy3(isize, L.isize);
+  copy3(istart, L.istart);
+  copy3(osize, L.osize);
+  copy3(ostart, L.ostart);
+  if (overflow_guard(L, sizeof_real)) return fail(ACCFFTB_ERR_OVERFLOW, "local block exceeds 2^31 elements");
+  return L.alloc_max;
+}
+
+long long accfftb_local_size_dft_c2c(const int n[3], const int c_dims[2], const int coords[2], int sizeof_real,
+                                     int isize[3], int istart[3], int osize[3], int ostart[3]) {
+  LocalSizes L = local_size_c2c(n, c_dims, coords, sizeof_real);
+  copy3(isize, L.isize);
+  copy3(istart, L.istart);
+  copy3(osize, L.osize);
+  copy3(ostart, L.ostart);
+  if (overflow_guard(L, sizeof_real)) return fail(ACCFFTB_ERR_OVERFLOW, "local block exceeds 2^31 elements");
+  return L.alloc_max;
+}
+
+int accfftb_stage_size(const int n[3], const int c_dims[2], const int coords[2], int kind, int sizeof_real, int which,
+                       int size[3], int start[3]) {
+  LocalSizes L = kind == ACCFFTB_R2C ? local_size_r2c(n, c_dims, coords, sizeof_real)
+                                     : local_size_c2c(n, c_dims, coords, sizeof_real);
+  const int zero[3] = {0, 0, 0};
+  switch (which) {
+    case 0: copy3(size, L.osize_0); copy3(start, L.ostart_0); return 0;
+    case 1: copy3(size, L.osize_1); copy3(start, L.ostart_1); return 0;
+    case 2: copy3(size, L.osize_2); copy3(start, L.ostart_2); return 0;
+    case 3: copy3(size, L.osize_y); copy3(start, L.ostart_y); return 0;
+    case 4: copy3(size, L.osize_yi); copy3(start, zero); return 0;
+    case 5: copy3(size, L.osize_x); copy3(start, zero); return 0;
+    case 6: copy3(size, L.osize_xi); copy3(start, zero); return 0;
+    default: return fail(ACCFFTB_ERR_ARG, "accfftb_stage_size: which must be 0..6");
+  }
+}
+
+int accfftb_length_supported(int n) { return length_supported(n) ? 1 : 0; }
+
+accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank, int kind, int prec, unsigned flags) {
+  (void)flags;   // ESTIMATE / MEASURE / PATIENT: there is a single exchange method, nothing to tune
+  if (!n || !c_dims || n[0] <= 0 || n[1] <= 0 || n[2] <= 0 || c_dims[0] <= 0 || c_dims[1] <= 0 || rank < 0 ||
+      rank >= c_dims[0] * c_dims[1] || (kind != ACCFFTB_R2C && kind != ACCFFTB_C2C) ||
+      (prec != ACCFFTB_DOUBLE && prec != ACCFFTB_FLOAT)) {
+    fail(ACCFFTB_ERR_ARG, "accfftb_plan_create: bad argument");
+    return nullptr;
+  }
+  accfftb_plan* p = new accfftb_plan();
+  Engine* e = &p->e;
+  e->be.e = e;
+  e->rank = rank;
+  int coords[2] = {rank / c_dims[1], rank % c_dims[1]};
+  Plan& pl = e->plan;
+  pl.g = make_geometry(n, c_dims, coords, kind == ACCFFTB_R2C, prec == ACCFFTB_DOUBLE ? 8 : 4);
+  pl.prec = (Prec)prec;
+  pl.inplace = false;
+  pl.be = &e->be;
+  pl.nprocs = c_dims[0] * c_dims[1];
+  if (!pl.check_supported()) {
+    fail(ACCFFTB_ERR_UNSUPPORTED, pl.error);
+    delete p;
+    return nullptr;
+  }
+  if (overflow_guard(pl.g.L, prec == ACCFFTB_DOUBLE ? 8 : 4)) {
+    fail(ACCFFTB_ERR_OVERFLOW, "local block exceeds 2^31 elements");
+    delete p;
+    return nullptr;
+  }
+  cudaError_t err = cudaGetDevice(&e->device);
+  if (err == cudaSuccess) {
+    e->bufsz = bufsz_of(e, rank);
+    e->slab_bytes = 2 * e->bufsz + kFlagBytes;
+    err = cudaMalloc((void**)&e->slab, e->slab_bytes);
+  }
+  if (err == cudaSuccess) err = cudaMemset(e->slab + 2 * e->bufsz, 0, kFlagBytes);
+  if (err == cudaSuccess) err = cudaMalloc((void**)&e->status_d, sizeof(int));
+  if (err == cudaSuccess) err = cudaMemset(e->status_d, 0, sizeof(int));
+  if (err == cudaSuccess) err = cudaEventCreate(&e->ev[0]);
+  if (err == cudaSuccess) err = cudaEventCreate(&e->ev[1]);
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    cuda_fail(err, "accfftb_plan_create");
+    engine_free(e);
+    delete p;
+    return nullptr;
+  }
+  wire_self(e);
+  e->wired = pl.nprocs == 1;
+  return p;
+}
+
+int accfftb_plan_ipc_export(accfftb_plan* plan, void* blob) {
+  if (!plan || !blob) return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_export: null argument");
+  Engine* e = &plan->e;
+  IpcBlob b;
+  memset(&b, 0, sizeof(b));
+  CU(cudaIpcGetMemHandle(&b.handle, e->slab));
+  b.slab_bytes = e->slab_bytes;
+  b.rank = e->rank;
+  b.nprocs = e->plan.nprocs;
+  b.magic = 0xACCFF7B2u;
+  memcpy(blob, &b, sizeof(b));
+  return 0;
+}
+
+int accfftb_plan_ipc_import(accfftb_plan* plan, const void* blobs, int nblobs) {
+  if (!plan || !blobs) return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: null argument");
+  Engine* e = &plan->e;
+  if (nblobs != e->plan.nprocs) return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: need one blob per rank");
+  if (e->wired && e->plan.nprocs > 1) return fail(ACCFFTB_ERR_STATE, "peers already attached");
+  for (int q = 0; q < nblobs; ++q) {
+    IpcBlob b;
+    memcpy(&b, (const char*)blobs + (size_t)q * sizeof(IpcBlob), sizeof(b));
+    if (b.magic != 0xACCFF7B2u || b.rank != q || b.nprocs != nblobs)
+      return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: blob " + std::to_string(q) + " is not rank-ordered / valid");
+    const size_t bs = bufsz_of(e, q);
+    if (b.slab_bytes != 2 * bs + kFlagBytes)
+      return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: peer plan geometry differs");
+    if (q == e->rank) continue;
+    void* base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
+    e->opened.push_back(base);
+    e->plan.peerA[q] = base;
+    e->plan.peerB[q] = (char*)base + bs;
+    e->flag_ptrs[q] = (unsigned long long*)((char*)base + 2 * bs);
+  }
+  e->wired = true;
+  return 0;
+}
+
+int accfftb_plan_attach_local_peers(accfftb_plan* plan, accfftb_plan* const* plans, int nplans) {
+  if (!plan || !plans) return fail(ACCFFTB_ERR_ARG, "accfftb_plan_attach_local_peers: null argument");
+  Engine* e = &plan->e;
+  if (nplans != e->plan.nprocs) return fail(ACCFFTB_ERR_ARG, "need one plan per rank");
+  CU(cudaSetDevice(e->device));
+  for (int q = 0; q < nplans; ++q) {
+    if (q == e->rank) continue;
+    Engine* o = &plans[q]->e;
+    if (o->rank != q) return fail(ACCFFTB_ERR_ARG, "plans are not rank-ordered");
+    if (o->device != e->device) {
+      cudaError_t err = cudaDeviceEnablePeerAccess(o->device, 0);
+      if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (err != cudaSuccess) return cuda_fail(err, "cudaDeviceEnablePeerAccess");
+    }
+    e->plan.peerA[q] = o->slab;
+    e->plan.peerB[q] = o->slab + o->bufsz;
+    e->flag_ptrs[q] = (unsigned long long*)(o->slab + 2 * o->bufsz);
+  }
+  e->wired = true;
+  return 0;
+}
+
+int accfftb_plan_set_stream(accfftb_plan* plan, void* cuda_stream) {
+  if (!plan) return fail(ACCFFTB_ERR_ARG, "null plan");
+  plan->e.stream = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+int accfftb_plan_set_blocking(accfftb_plan* plan, int blocking) {
+  if (!plan) return fail(ACCFFTB_ERR_ARG, "null plan");
+  plan->e.blocking = blocking != 0;
+  return 0;
+}
+
+long long accfftb_plan_alloc_max(const accfftb_plan* plan) { return plan ? plan->e.plan.g.L.alloc_max : -1; }
+long long accfftb_plan_launch_count(const accfftb_plan* plan) { return plan ? plan->e.launches : -1; }
+
+int accfftb_plan_destroy(accfftb_plan* plan) {
+  if (!plan) return 0;
+  engine_free(&plan->e);
+  delete plan;
+  return 0;
+}
+
+#define CHECK_PLAN(plan, want_r2c)                                                                  \
+  if (!(plan)) return fail(ACCFFTB_ERR_ARG, "null plan");                                          \
+  if ((plan)->e.plan.g.r2c != (want_r2c))                                                           \
+    return fail(ACCFFTB_ERR_ARG, (want_r2c) ? "this call needs an r2c plan" : "this call needs a c2c plan"); \
+  if (xyz != 7) return fail(ACCFFTB_ERR_UNSUPPORTED, "partial-axis transforms (xyz != 111) are not implemented");
+
+int accfftb_execute_r2c(accfftb_plan* plan, const void* data, void* data_out, double* timer, int xyz) {
+  CHECK_PLAN(plan, true);
+  if (!data || !data_out) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 5);
+  return engine_finish(e, e->plan.execute_forward(data, data_out, data == data_out));
+}
+
+int accfftb_execute_c2r(accfftb_plan* plan, const void* data, void* data_out, double* timer, int xyz) {
+  CHECK_PLAN(plan, true);
+  if (!data || !data_out) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 5);
+  return engine_finish(e, e->plan.execute_inverse(data, data_out, data == data_out));
+}
+
+int accfftb_execute_c2c(accfftb_plan* plan, int direction, const void* data, void* data_out, double* timer, int xyz) {
+  CHECK_PLAN(plan, false);
+  if (!data || !data_out) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  if (direction != ACCFFTB_FORWARD && direction != ACCFFTB_BACKWARD)
+    return fail(ACCFFTB_ERR_ARG, "direction must be ACCFFTB_FORWARD or ACCFFTB_BACKWARD");
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 5);
+  if (direction == ACCFFTB_FORWARD) return engine_finish(e, e->plan.execute_forward(data, data_out, false));
+  return engine_finish(e, e->plan.execute_inverse(data, data_out, false));
+}
+
+static int ensure_spec(Engine* e) {
+  if (e->spec) return 0;
+  CU(cudaMalloc(&e->spec, e->bufsz));
+  return 0;
+}
+
+int accfftb_laplace(accfftb_plan* plan, const void* A, void* LA, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, true);
+  if (!A || !LA) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 7);
+  return engine_finish(e, e->plan.execute_spectral(A, LA, OP_LAPLACE));
+}
+
+int accfftb_biharmonic(accfftb_plan* plan, const void* A, void* BA, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, true);
+  if (!A || !BA) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 7);
+  return engine_finish(e, e->plan.execute_spectral(A, BA, OP_BIHARMONIC));
+}
+
+int accfftb_grad(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int comps, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, true);
+  if (!A) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  if (((comps & 1) && !Ax) || ((comps & 2) && !Ay) || ((comps & 4) && !Az))
+    return fail(ACCFFTB_ERR_ARG, "selected gradient component has a null output pointer");
+  Engine* e = &plan->e;
+  int rc = ensure_spec(e);
+  if (rc) return rc;
+  TimerScope ts(e, timer, 7);
+  void* outs[3] = {Ax, Ay, Az};
+  return engine_finish(e, e->plan.execute_grad(A, outs, comps, e->spec));
+}
+
+int accfftb_divergence(accfftb_plan* plan, const void* Ax, const void* Ay, const void* Az, void* div, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, true);
+  if (!Ax || !Ay || !Az || !div) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  Engine* e = &plan->e;
+  int rc = ensure_spec(e);
+  if (rc) return rc;
+  TimerScope ts(e, timer, 7);
+  const void* ins[3] = {Ax, Ay, Az};
+  return engine_finish(e, e->plan.execute_divergence(ins, div, e->spec));
+}
+
+}  // extern "C"

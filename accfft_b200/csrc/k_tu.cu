@@ -1,0 +1,17 @@
+// k_tu.cu -- compiled once per (ACCFFT_KIND, ACCFFT_PREC) pair (see Makefile): instantiates the stage
+// kernels of that kind / precision for every schedule and exports one launcher.
+//   ACCFFT_KIND: 0 strided c2c (Y and X passes), 1 contiguous c2c (Z pass of c2c plans),
+//                2 contiguous r2c, 3 contiguous c2r (Z pass of r2c plans)
+//   ACCFFT_PREC: 0 double, 1 float
+#include "launch_impl.cuh"
+
+#define ACCFFT_CAT3(a, b, c, d) a##b##c##d
+#define ACCFFT_NAME(k, p) ACCFFT_CAT3(accfft_launch_k, k, _p, p)
+
+namespace accfft_b200 {
+#if ACCFFT_PREC == 0
+int ACCFFT_NAME(ACCFFT_KIND, ACCFFT_PREC)(const Launch& l, cudaStream_t st) { return launch_any<double>(l, st); }
+#else
+int ACCFFT_NAME(ACCFFT_KIND, ACCFFT_PREC)(const Launch& l, cudaStream_t st) { return launch_any<float>(l, st); }
+#endif
+}  // namespace accfft_b200

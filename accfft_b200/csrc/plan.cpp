@@ -321,4 +321,70 @@ int Plan::execute_spectral(const void* in, void* out, int op) {
   return 0;
 }
 
+int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spec) {
+  int rc;
+  const double inv_n = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
+  Launch z = fwd_z(in, false);
+  if (!empty(z) && (rc = be->launch(z))) return rc;
+  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  Launch y = fwd_y();
+  if (!empty(y) && (rc = be->launch(y))) return rc;
+  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  Launch x = fwd_x(spec);
+  x.desc.op = OP_SCALE;
+  x.desc.scale = inv_n;
+  if (!empty(x) && (rc = be->launch(x))) return rc;
+  for (int ax = 0; ax < 3; ++ax) {
+    if (!(comps & (1 << ax))) continue;
+    Launch xi = inv_x(spec);
+    // same (k0, k1, k2) bookkeeping as the forward X stage: the layouts are identical
+    for (int i = 0; i < 3; ++i) {
+      xi.desc.n[i] = x.desc.n[i];
+      xi.desc.kind[i] = x.desc.kind[i];
+      xi.desc.off[i] = x.desc.off[i];
+    }
+    xi.desc.div = x.desc.div;
+    xi.desc.op = OP_GRAD;
+    xi.desc.opAxis = ax;
+    xi.desc.scale = 1.0;
+    xi.desc.opOnLoad = 1;
+    if (!empty(xi) && (rc = be->launch(xi))) return rc;
+    if (nprocs > 1 && (rc = be->barrier())) return rc;
+    Launch yi = inv_y();
+    if (!empty(yi) && (rc = be->launch(yi))) return rc;
+    if (nprocs > 1 && (rc = be->barrier())) return rc;
+    Launch zi = inv_z(outs[ax], false);
+    if (!empty(zi) && (rc = be->launch(zi))) return rc;
+  }
+  return 0;
+}
+
+int Plan::execute_divergence(const void* const ins[3], void* out, void* spec) {
+  int rc;
+  const double inv_n = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
+  for (int ax = 0; ax < 3; ++ax) {
+    Launch z = fwd_z(ins[ax], false);
+    if (!empty(z) && (rc = be->launch(z))) return rc;
+    if (nprocs > 1 && (rc = be->barrier())) return rc;
+    Launch y = fwd_y();
+    if (!empty(y) && (rc = be->launch(y))) return rc;
+    if (nprocs > 1 && (rc = be->barrier())) return rc;
+    Launch x = fwd_x(spec);
+    x.desc.op = OP_GRAD;
+    x.desc.opAxis = ax;
+    x.desc.scale = inv_n;
+    x.desc.accumulate = ax > 0;
+    if (!empty(x) && (rc = be->launch(x))) return rc;
+  }
+  Launch xi = inv_x(spec);
+  if (!empty(xi) && (rc = be->launch(xi))) return rc;
+  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  Launch yi = inv_y();
+  if (!empty(yi) && (rc = be->launch(yi))) return rc;
+  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  Launch zi = inv_z(out, false);
+  if (!empty(zi) && (rc = be->launch(zi))) return rc;
+  return 0;
+}
+
 }  // namespace accfft_b200

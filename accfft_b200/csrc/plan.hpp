@@ -71,6 +71,12 @@ struct Plan {
   int execute_inverse(const void* in, void* out, bool out_padded);
   // fused forward -> spectral symbol -> inverse (laplace / biharmonic; src/operators_gpu.txx:280-334, :555-609)
   int execute_spectral(const void* in, void* out, int op);
+  // grad (src/operators_gpu.txx:72-278): one forward into `spec` (normalised), then per selected component
+  // an inverse whose X stage multiplies by i*k_axis on load.  comps: bit 0 = x, bit 1 = y, bit 2 = z.
+  int execute_grad(const void* in, void* const outs[3], int comps, void* spec);
+  // divergence (src/operators_gpu.txx:336-553): three forwards whose X stage multiplies by i*k_axis and
+  // accumulates into `spec`, then one inverse.
+  int execute_divergence(const void* const ins[3], void* out, void* spec);
 };
 
 unsigned blk_magic(int blk);

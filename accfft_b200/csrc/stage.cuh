@@ -50,7 +50,18 @@ struct StageDesc {
   int off[3];
   int div;
   double scale;
+  int opOnLoad;          // 1: apply `op` to the INPUT elements (inverse X stage of grad) instead of the outputs
+  int accumulate;        // 1: outputs are added to the destination (divergence sums three spectra)
 };
+
+template <class T>
+ACC_HD void store_out(const StageDesc& d, cplx<T>* dst, cplx<T> y) {
+  if (d.accumulate) {
+    const cplx<T> o = *dst;
+    y = {o.x + y.x, o.y + y.y};
+  }
+  *dst = y;
+}
 
 ACC_HD int seg_of(const StageDesc& d, int k) {
   if (d.nseg == 1) return 0;
@@ -115,6 +126,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
     const long long si = d.inStrideI;
     pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) {
       cplx<T> x = in[(long long)i * si];
+      if (d.opOnLoad) x = apply_op(d, x, i, a, b);
       r = INV ? cswap(x) : x;
     });
   }
@@ -128,7 +140,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
       cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB +
                      (long long)(k - s * d.blk) * sd.strideI;
       cplx<T> y = INV ? cswap(r) : r;
-      *dst = apply_op(d, y, k, a, b);
+      store_out(d, dst, d.opOnLoad ? y : apply_op(d, y, k, a, b));
     });
   }
 }

@@ -1,0 +1,150 @@
+/* accfft_b200.h -- C ABI of libaccfft_b200.so: the B200-native engine behind AccFFT's GPU API.
+ *
+ * Plain C, plain pointers and sizes.  Every entry point names the reference interface it replaces
+ * (paths relative to the AccFFT source tree).  The C++ header include/accfft_gpu.h re-creates the
+ * reference's own C++ API (same names / argument meaning) on top of these calls; accfft_b200/api.py
+ * is the ctypes binding used by the tests and the benchmark.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers on the CUDA device that was current when the plan was
+ *     created (one rank <-> one GPU, chosen by the caller exactly as with the reference, which never
+ *     calls cudaSetDevice);
+ *   - calls on a plan are collective over the plan's P0 x P1 process grid;
+ *   - return value 0 = success; otherwise a negative accfftb error or a positive cudaError_t, with
+ *     accfftb_last_error() returning a message for the calling thread;
+ *   - transforms are unnormalised (c2r(r2c(x)) = N0*N1*N2*x) like the reference;
+ *   - prec: 0 = double (accfft_*_gpu), 1 = float (accfft_*_gpuf).
+ */
+#ifndef ACCFFT_B200_H
+#define ACCFFT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct accfftb_plan accfftb_plan;
+
+#define ACCFFTB_FORWARD (-1) /* ACCFFT_FORWARD,  include/accfft_common.h:38 */
+#define ACCFFTB_BACKWARD (+1) /* ACCFFT_BACKWARD, include/accfft_common.h:39 */
+#define ACCFFTB_ESTIMATE 1    /* ACCFFT_ESTIMATE, include/accfft_common.h:40 */
+#define ACCFFTB_MEASURE 2     /* ACCFFT_MEASURE,  include/accfft_common.h:41 */
+#define ACCFFTB_PATIENT 4     /* ACCFFT_PATIENT,  include/accfft_common.h:42 */
+
+#define ACCFFTB_R2C 0
+#define ACCFFTB_C2C 1
+#define ACCFFTB_DOUBLE 0
+#define ACCFFTB_FLOAT 1
+
+#define ACCFFTB_IPC_BLOB_BYTES 128 /* per-rank blob exchanged by accfftb_plan_ipc_export / _import */
+#define ACCFFTB_MAX_GROUP 16       /* max ranks along one dimension of the process grid */
+
+#define ACCFFTB_ERR_ARG (-1)         /* bad argument */
+#define ACCFFTB_ERR_UNSUPPORTED (-2) /* no kernel schedule for a transform length, odd N2 for r2c, ... */
+#define ACCFFTB_ERR_STATE (-3)       /* e.g. multi-rank plan executed before accfftb_plan_ipc_import */
+#define ACCFFTB_ERR_TIMEOUT (-4)     /* inter-GPU barrier timed out (a peer died or diverged) */
+#define ACCFFTB_ERR_OVERFLOW (-5)    /* local block exceeds 2^31 elements: src/accfft_common.cpp:179-184 */
+
+const char* accfftb_last_error(void);
+const char* accfftb_version(void);
+
+/* ---- process grid and pencil decomposition (host integer math only; no GPU needed) ------------ */
+
+/* The MPI_Dims_create fallback of accfft_create_comm (src/accfft_common.cpp:281-289): if
+ * c_dims[0]*c_dims[1] != nprocs the dims are OVERWRITTEN with a balanced, non-increasing
+ * factorisation (2 -> 2x1, 4 -> 2x2, 8 -> 4x2).  Returns 1 if c_dims was overwritten, 0 if kept. */
+int accfftb_create_comm_dims(int nprocs, int c_dims[2]);
+
+/* Cartesian rank -> (coord0, coord1), row-major as MPI_Cart_create(reorder ignored) lays them out
+ * (src/accfft_common.cpp:298): rank = coord0 * c_dims[1] + coord1. */
+void accfftb_rank_to_coords(int rank, const int c_dims[2], int coords[2]);
+
+/* accfft_local_size_dft_r2c_gpu / _gpuf  (src/accfft_gpu.cpp:62-65 -> src/accfft_common.cpp:98-192).
+ * sizeof_real = 8 (double API) or 4 (float API).  Returns alloc_max in BYTES (64-bit here; the
+ * reference returns int) or ACCFFTB_ERR_OVERFLOW. */
+long long accfftb_local_size_dft_r2c(const int n[3], const int c_dims[2], const int coords[2], int sizeof_real,
+                                     int isize[3], int istart[3], int osize[3], int ostart[3]);
+
+/* accfft_local_size_dft_c2c_gpu / _gpuf  (src/accfft_gpu.cpp:689-692 -> src/accfft_common.cpp:203-256). */
+long long accfftb_local_size_dft_c2c(const int n[3], const int c_dims[2], const int coords[2], int sizeof_real,
+                                     int isize[3], int istart[3], int osize[3], int ostart[3]);
+
+/* Stage geometry the reference keeps in the public plan struct (include/accfft_gpu.h:37-95):
+ * which = 0,1,2 -> osize_0/1/2 + ostart_0/1/2;  3 -> osize_y/ostart_y;  4 -> osize_yi;  5 -> osize_x;
+ * 6 -> osize_xi.  start may be NULL. */
+int accfftb_stage_size(const int n[3], const int c_dims[2], const int coords[2], int kind, int sizeof_real,
+                       int which, int size[3], int start[3]);
+
+/* 1 if a transform of this length is available along an axis (mixed radix 2/3/5 schedules), else 0.
+ * r2c plans need N2 even with N2/2 supported; every other axis needs its own length supported. */
+int accfftb_length_supported(int n);
+
+/* ---- plans ------------------------------------------------------------------------------------ */
+
+/* accfft_plan_dft_3d_r2c_gpu / _gpuf (src/accfft_gpu.cpp:77-442) and accfft_plan_dft_3d_c2c_gpu / _gpuf
+ * (:704-931).  kind = ACCFFTB_R2C / ACCFFTB_C2C.  The plan owns two exchange buffers of alloc_max bytes
+ * on the current device (the reference's Mem_Mgr_gpu owns three device + two pinned host buffers,
+ * src/transpose_gpu.cpp:58-131) and the twiddle tables.  Unlike the reference, plan creation never
+ * touches user data (ACCFFT_MEASURE clobbers data_out there, src/accfft_gpu.cpp:382-386) so no data
+ * pointers are taken.  Returns NULL on failure (as the reference does, :187-191). */
+accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank, int kind, int prec, unsigned flags);
+
+/* Multi-GPU wiring (replaces MPI_Comm_split + the host-staged MPI_Alltoall[v] machinery of
+ * src/transpose_gpu.cpp:3940-3955): each rank exports a blob (CUDA IPC handle of its exchange slab),
+ * the caller all-gathers the blobs over ANY transport (torch.distributed, MPI, files ...) and hands the
+ * rank-ordered array to _import, which maps every peer's slab over NVLink.  Single-rank plans skip both. */
+int accfftb_plan_ipc_export(accfftb_plan* plan, void* blob);
+int accfftb_plan_ipc_import(accfftb_plan* plan, const void* blobs, int nblobs);
+/* Same wiring for ranks that live in ONE process (one host thread per GPU): hand over the peers' plan
+ * handles instead of IPC blobs; peer access is enabled with cudaDeviceEnablePeerAccess. */
+int accfftb_plan_attach_local_peers(accfftb_plan* plan, accfftb_plan* const* plans, int nplans);
+
+/* CUDA stream (cudaStream_t) the plan's kernels are enqueued on; default: the legacy default stream,
+ * as in the reference.  blocking = 1 (default) makes every execute / operator call return only when
+ * the device has finished, like the reference (cudaDeviceSynchronize, src/accfft_gpu.cpp:620);
+ * blocking = 0 only enqueues. */
+int accfftb_plan_set_stream(accfftb_plan* plan, void* cuda_stream);
+int accfftb_plan_set_blocking(accfftb_plan* plan, int blocking);
+
+long long accfftb_plan_alloc_max(const accfftb_plan* plan);
+/* number of kernels the plan has launched so far (stage kernels + inter-GPU barrier kernels) */
+long long accfftb_plan_launch_count(const accfftb_plan* plan);
+
+/* accfft_destroy_plan_gpu / accfft_destroy_plan (src/accfft_gpu.cpp:1150-1192); frees everything the
+ * plan owns (the reference leaks the plan object and T_plan_x/xi).  NULL is accepted. */
+int accfftb_plan_destroy(accfftb_plan* plan);
+
+/* ---- execution (device pointers) ---------------------------------------------------------------
+ * timer: NULL or double[5], accumulated (+=) with the reference's meaning (doc/timing.md):
+ *   [0] exchange total, [1] pack, [2] communication, [3] unpack, [4] local FFT, all in seconds.
+ *   Pack and unpack are fused into the FFT kernels here, so [1] = [3] = 0 and [0] = [2] = time spent in
+ *   the inter-GPU barriers; [4] = time in the stage kernels (which includes their NVLink stores).
+ * xyz: bit 2 = Z, bit 1 = Y, bit 0 = X like the std::bitset<3> of the reference
+ *   (src/accfft_gpu.cpp:477,499,527); only 7 (all axes) is implemented, anything else returns
+ *   ACCFFTB_ERR_UNSUPPORTED.
+ */
+
+/* accfft_execute_r2c_gpu / _gpuf (src/accfft_gpu.cpp:635-649): real [isize] (rows of N2 reals, or of
+ * 2*(N2/2+1) when data_out == data, i.e. in place) -> complex [osize]. */
+int accfftb_execute_r2c(accfftb_plan* plan, const void* data, void* data_out, double* timer, int xyz);
+/* accfft_execute_c2r_gpu / _gpuf (:661-675): complex [osize] -> real [isize].  Unlike the reference
+ * (:544-545) the input spectrum is NOT overwritten. */
+int accfftb_execute_c2r(accfftb_plan* plan, const void* data, void* data_out, double* timer, int xyz);
+/* accfft_execute_c2c_gpu / _gpuf (:943-1136): direction = ACCFFTB_FORWARD / ACCFFTB_BACKWARD. */
+int accfftb_execute_c2c(accfftb_plan* plan, int direction, const void* data, void* data_out, double* timer, int xyz);
+
+/* ---- spectral operators (accfft_operators_gpu.h:44-67; src/operators_gpu.txx; kernels
+ * src/operators_cuda.cu:15-215).  Real [isize] in, real [isize] out, normalised, Nyquist modes zeroed.
+ * The symbol multiply and the 1/N scale are fused into the X-pass stores (no Hadamard kernels, no
+ * per-call cudaMalloc).  Need an r2c plan.  timer: NULL or double[7] (the reference's operators write
+ * index 6). */
+int accfftb_laplace(accfftb_plan* plan, const void* A, void* LA, double* timer);
+int accfftb_biharmonic(accfftb_plan* plan, const void* A, void* BA, double* timer);
+/* xyz selects components: bit 0 = x (Ax), bit 1 = y (Ay), bit 2 = z (Az), as grad_gpu's std::bitset<3>*
+ * (src/operators_gpu.txx:172-278); unselected outputs may be NULL. */
+int accfftb_grad(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int xyz, double* timer);
+int accfftb_divergence(accfftb_plan* plan, const void* Ax, const void* Ay, const void* Az, void* div, double* timer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACCFFT_B200_H */
