@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     Comm,
     Plan,
     accfft_create_comm,
+    attach_local_peers,
     accfft_local_size_dft_c2c_gpu,
     accfft_local_size_dft_c2c_gpuf,
     accfft_local_size_dft_r2c_gpu,

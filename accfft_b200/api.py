@@ -70,6 +70,8 @@ def lib():
     L.accfftb_plan_attach_local_peers.argtypes = [c_vp, ctypes.POINTER(c_vp), c_int]
     L.accfftb_plan_set_stream.argtypes = [c_vp, c_vp]
     L.accfftb_plan_set_blocking.argtypes = [c_vp, c_int]
+    L.accfftb_plan_set_profiling.argtypes = [c_vp, c_int]
+    L.accfftb_plan_profile_read.argtypes = [c_vp, c_dp, ctypes.POINTER(c_ll)]
     L.accfftb_plan_alloc_max.restype = c_ll
     L.accfftb_plan_alloc_max.argtypes = [c_vp]
     L.accfftb_plan_launch_count.restype = c_ll
@@ -198,8 +200,9 @@ def _ptr(t) -> int:
 class Plan:
     """accfft_plan_gpu / accfft_plan_gpuf."""
 
-    def __init__(self, n, comm: Comm, r2c: bool, single: bool, flags: int = ACCFFT_ESTIMATE):
+    def __init__(self, n, comm: Comm, r2c: bool, single: bool, flags: int = ACCFFT_ESTIMATE, wire: bool = True):
         self.n, self.comm, self.r2c, self.single = tuple(int(x) for x in n), comm, r2c, single
+        self._local_group = None
         L = lib()
         self._h = L.accfftb_plan_create(_i3(n), _i2(comm.c_dims), comm.rank, _R2C if r2c else _C2C,
                                         _FLOAT if single else _DOUBLE, flags)
@@ -209,7 +212,7 @@ class Plan:
         sz = (accfft_local_size_dft_r2c_gpuf if single else accfft_local_size_dft_r2c_gpu) if r2c else \
              (accfft_local_size_dft_c2c_gpuf if single else accfft_local_size_dft_c2c_gpu)
         self.alloc_max, self.isize, self.istart, self.osize, self.ostart = sz(n, comm)
-        if comm.nprocs > 1:
+        if comm.nprocs > 1 and wire:
             blob = ctypes.create_string_buffer(_BLOB)
             _check(L.accfftb_plan_ipc_export(self._h, blob), "accfftb_plan_ipc_export")
             blobs = b"".join(comm.all_gather_bytes(blob.raw))
@@ -223,6 +226,18 @@ class Plan:
 
     def set_blocking(self, blocking: bool):
         _check(lib().accfftb_plan_set_blocking(self._h, int(blocking)), "set_blocking")
+
+    def set_profiling(self, on: bool):
+        _check(lib().accfftb_plan_set_profiling(self._h, int(on)), "set_profiling")
+
+    PROFILE_SLOTS = ("fwd_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "inv_z", "barrier")
+
+    def profile_read(self):
+        """-> {slot name: (total ms, launches)} since the last read (synchronises the plan's stream)"""
+        ms = (ctypes.c_double * 7)()
+        cnt = (ctypes.c_longlong * 7)()
+        _check(lib().accfftb_plan_profile_read(self._h, ms, cnt), "profile_read")
+        return {name: (ms[i], int(cnt[i])) for i, name in enumerate(self.PROFILE_SLOTS)}
 
     @property
     def launch_count(self) -> int:
@@ -287,7 +302,7 @@ class Plan:
     def destroy(self):
         """accfft_destroy_plan_gpu(plan)"""
         if getattr(self, "_h", None):
-            if self.comm.nprocs > 1:
+            if self.comm.nprocs > 1 and self._local_group is None:
                 try:
                     import torch
                     torch.cuda.synchronize()
@@ -304,6 +319,16 @@ class Plan:
                 self._h = None
         except Exception:
             pass
+
+
+def attach_local_peers(plans: Sequence[Plan]):
+    """Wire plans whose ranks all live in THIS process (one host thread per rank, created with wire=False):
+    peers' exchange slabs are addressed directly (cudaDeviceEnablePeerAccess between devices) instead of
+    through CUDA IPC.  plans must be in rank order."""
+    arr = (ctypes.c_void_p * len(plans))(*[p._h for p in plans])
+    for p in plans:
+        _check(lib().accfftb_plan_attach_local_peers(p._h, arr, len(plans)), "accfftb_plan_attach_local_peers")
+        p._local_group = list(plans)
 
 
 def accfft_plan_dft_3d_r2c_gpu(n, comm: Comm, flags: int = ACCFFT_ESTIMATE) -> Plan:

@@ -120,6 +120,43 @@ struct Engine {
   // timing of the current call
   bool timing = false;
   double t_fft = 0, t_bar = 0;
+  // per-launch profiling (event pairs on the plan's stream, read back by accfftb_plan_profile_read)
+  bool profiling = false;
+  struct Rec {
+    int slot;
+    cudaEvent_t a, b;
+  };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t take_event() {
+    if (!pool.empty()) {
+      cudaEvent_t ev = pool.back();
+      pool.pop_back();
+      return ev;
+    }
+    cudaEvent_t ev = nullptr;
+    cudaEventCreate(&ev);
+    return ev;
+  }
+};
+
+struct ScopedProfile {
+  Engine* e;
+  Engine::Rec r;
+  ScopedProfile(Engine* e_, int slot) : e(e_) {
+    if (e->profiling) {
+      r.slot = slot;
+      r.a = e->take_event();
+      r.b = e->take_event();
+      cudaEventRecord(r.a, e->stream);
+    }
+  }
+  ~ScopedProfile() {
+    if (e->profiling) {
+      cudaEventRecord(r.b, e->stream);
+      e->recs.push_back(r);
+    }
+  }
 };
 
 const void* CudaBackend::twiddle(Prec prec, int M) {
@@ -167,6 +204,7 @@ struct ScopedTimer {
 int CudaBackend::launch(const Launch& l) {
   if (!l.desc.tw) return fail(ACCFFTB_ERR_STATE, "twiddle table allocation failed");
   ScopedTimer tm(e, &e->t_fft);
+  ScopedProfile pf(e, l.slot);
   int rc = -1;
   const int sel = (int)l.kind * 2 + (int)l.prec;
   switch (sel) {
@@ -189,6 +227,7 @@ int CudaBackend::launch(const Launch& l) {
 int CudaBackend::barrier() {
   if (!e->wired) return fail(ACCFFTB_ERR_STATE, "multi-rank plan used before its peers were attached");
   ScopedTimer tm(e, &e->t_bar);
+  ScopedProfile pf(e, 6);
   BarrierDesc b;
   memset(&b, 0, sizeof(b));
   for (int q = 0; q < e->plan.nprocs; ++q) b.flags[q] = e->flag_ptrs[q];
@@ -210,7 +249,8 @@ static int engine_finish(Engine* e, int rc) {
     CU(cudaStreamSynchronize(e->stream));
     if (e->plan.nprocs > 1) {
       int st = 0;
-      CU(cudaMemcpy(&st, e->status_d, sizeof(int), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpyAsync(&st, e->status_d, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
       if (st) return fail(ACCFFTB_ERR_TIMEOUT, "inter-GPU barrier timed out");
     }
   }
@@ -228,6 +268,8 @@ static void engine_free(Engine* e) {
   if (e->status_d) cudaFree(e->status_d);
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
   if (e->ev[1]) cudaEventDestroy(e->ev[1]);
+  for (auto& r : e->recs) cudaEventDestroy(r.a), cudaEventDestroy(r.b);
+  for (auto ev : e->pool) cudaEventDestroy(ev);
 }
 
 static void wire_self(Engine* e) {
@@ -284,9 +326,9 @@ struct accfftb_plan {
   Engine e;
 };
 
-static bool overflow_guard(const LocalSizes& L, int sizeof_real) {
-  // the reference refuses local blocks of more than 2^31 elements (src/accfft_common.cpp:179-184)
-  return L.alloc_max / sizeof_real > (1LL << 31);
+static bool overflow_guard(const LocalSizes& L, int) {
+  // the reference refuses local input blocks of more than 2^31-1 elements (src/accfft_common.cpp:179-184)
+  return (long long)L.isize[0] * L.isize[1] * L.isize[2] > 2147483647LL;
 }
 
 extern "C" {
@@ -328,7 +370,7 @@ long long accfftb_local_size_dft_c2c(const int n[3], const int c_dims[2], const 
   copy3(istart, L.istart);
   copy3(osize, L.osize);
   copy3(ostart, L.ostart);
-  if (overflow_guard(L, sizeof_real)) return fail(ACCFFTB_ERR_OVERFLOW, "local block exceeds 2^31 elements");
+  // (the reference's c2c query has no overflow guard, src/accfft_common.cpp:203-256; sizes are 64-bit here)
   return L.alloc_max;
 }
 
@@ -375,8 +417,9 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
     delete p;
     return nullptr;
   }
-  if (overflow_guard(pl.g.L, prec == ACCFFTB_DOUBLE ? 8 : 4)) {
-    fail(ACCFFTB_ERR_OVERFLOW, "local block exceeds 2^31 elements");
+  if ((long long)pl.g.n[0] * pl.g.k1.size * pl.g.k2.size > 2147483647LL ||
+      (long long)pl.g.i0.size * pl.g.n[1] * pl.g.k2.size > 2147483647LL || overflow_guard(pl.g.L, 0)) {
+    fail(ACCFFTB_ERR_OVERFLOW, "local block exceeds 2^31 elements; use more ranks");
     delete p;
     return nullptr;
   }
@@ -473,6 +516,28 @@ int accfftb_plan_set_stream(accfftb_plan* plan, void* cuda_stream) {
 int accfftb_plan_set_blocking(accfftb_plan* plan, int blocking) {
   if (!plan) return fail(ACCFFTB_ERR_ARG, "null plan");
   plan->e.blocking = blocking != 0;
+  return 0;
+}
+
+int accfftb_plan_set_profiling(accfftb_plan* plan, int on) {
+  if (!plan) return fail(ACCFFTB_ERR_ARG, "null plan");
+  plan->e.profiling = on != 0;
+  return 0;
+}
+
+int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOTS], long long count[ACCFFTB_PROFILE_SLOTS]) {
+  if (!plan || !ms || !count) return fail(ACCFFTB_ERR_ARG, "null argument");
+  Engine* e = &plan->e;
+  CU(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < ACCFFTB_PROFILE_SLOTS; ++i) ms[i] = 0, count[i] = 0;
+  for (auto& r : e->recs) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, r.a, r.b));
+    if (r.slot >= 0 && r.slot < ACCFFTB_PROFILE_SLOTS) ms[r.slot] += t, count[r.slot]++;
+    e->pool.push_back(r.a);
+    e->pool.push_back(r.b);
+  }
+  e->recs.clear();
   return 0;
 }
 

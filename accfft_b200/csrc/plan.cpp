@@ -78,6 +78,7 @@ Launch Plan::fwd_z(const void* in, bool in_padded) const {
   l.prec = prec;
   l.inverse = false;
   l.desc = d;
+  l.slot = 0;
   return l;
 }
 
@@ -108,6 +109,7 @@ Launch Plan::fwd_y() const {
   l.fftN = g.n[1];
   l.inverse = false;
   l.desc = d;
+  l.slot = 1;
   return l;
 }
 
@@ -144,6 +146,7 @@ Launch Plan::fwd_x(void* out) const {
   l.fftN = g.n[0];
   l.inverse = false;
   l.desc = d;
+  l.slot = 2;
   return l;
 }
 
@@ -173,6 +176,7 @@ Launch Plan::inv_x(const void* in) const {
   l.fftN = g.n[0];
   l.inverse = true;
   l.desc = d;
+  l.slot = 3;
   return l;
 }
 
@@ -203,6 +207,7 @@ Launch Plan::inv_y() const {
   l.fftN = g.n[1];
   l.inverse = true;
   l.desc = d;
+  l.slot = 4;
   return l;
 }
 
@@ -236,6 +241,7 @@ Launch Plan::inv_z(void* out, bool out_padded) const {
   l.prec = prec;
   l.inverse = true;
   l.desc = d;
+  l.slot = 5;
   return l;
 }
 

@@ -20,6 +20,7 @@ struct Launch {
   Prec prec;
   int fftN;        // length of the complex engine transform (M = N/2 for r2c / c2r)
   bool inverse;
+  int slot;        // profiling slot: 0 fwd Z, 1 fwd Y, 2 fwd X, 3 inv X, 4 inv Y, 5 inv Z  (6 = barrier)
   StageDesc desc;
 };
 

@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of accfft_b200 (BASELINE.json): 3D r2c+c2r round trip at 512^3 double,
+GFLOP/s with FLOPs = 5 N log2 N per transform (N = N0 N1 N2; the same count for r2c and c2r), on 1/2/4/8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward r2c + one inverse c2r of the whole grid (strong scaling: the 512^3 grid is split
+over the N ranks as a P0 x P1 pencil grid).  Prints ONE JSON line on rank 0.
+
+  value     device-timed (CUDA events on the plan's stream, max over ranks), inputs resident in HBM
+  e2e       same metric through the public API with HOST buffers: pinned H2D of the input field and D2H of
+            the round-trip field inside the timed region, every step
+  roofline  the dominant stage kernel: algorithmic HBM bytes per launch / its mean launch duration (event
+            pairs recorded around every launch inside the timed region) vs the measured HBM copy peak
+  cpu_baseline / --impl reference: the CPU oracle port (pocketfft via scipy.fft, all host threads) -- the
+            reference's own FFTW+MPI path cannot be built in this image (no MPI, no FFTW)
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}   # BASELINE.json configs: 2x4 pencil grid on 8 GPUs
+
+
+def flops_per_transform(n):
+    N = n[0] * n[1] * n[2]
+    return 5.0 * N * math.log2(N)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period, self.stop_flag = index, period, False
+        self.sm, self.reasons, self.sm_max, self.err = [], set(), None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+                nv.nvmlClocksThrottleReasonApplicationsClocksSetting: "applications_clocks_setting",
+            }
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "error": self.err}
+        s = sorted(self.sm)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_roundtrip(n, workers, x=None):
+    from oracle import accfft_oracle as orc
+    if x is None:
+        x = orc.cpu_input(n)
+    t, _w = orc.cpu_roundtrip_seconds(n, workers=workers, x=x)
+    return t
+
+
+def run_reference(args):
+    from oracle import accfft_oracle as orc
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_full = (args.n, args.n, args.n)
+    n_small = (min(256, args.n),) * 3
+    cpu_roundtrip((64, 64, 64), cores)                      # spin up the pocketfft thread pool
+    t_small = cpu_roundtrip(n_small, cores)
+    budget = 150.0
+    total = args.steps + args.warmup
+    scale = (args.n / n_small[0]) ** 3 * 1.15
+    if t_small * scale * total <= budget:
+        n = n_full
+    elif t_small * total <= budget:
+        n = n_small
+    else:
+        n = (128, 128, 128)
+    x = orc.cpu_input(n)
+    for _ in range(args.warmup):
+        cpu_roundtrip(n, cores, x)
+    dt = sum(cpu_roundtrip(n, cores, x) for _ in range(args.steps)) / max(args.steps, 1)
+    gf = 2 * flops_per_transform(n) / dt / 1e9
+    sample = "%d^3 double r2c+c2r round trip per step (scipy.fft pocketfft, workers=%d)" % (n[0], cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%d^3 double r2c+c2r round trip" % args.n, "sample": sample,
+                   "note": "CPU oracle port; the reference's FFTW+MPI path cannot be built here (no MPI, no FFTW)"},
+        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+METRIC = "3D r2c+c2r GFLOP/s (5N*log2N per transform) at 512^3 double"
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="grid edge (default: the headline 512)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import accfft_b200 as acc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    n = (args.n, args.n, args.n)
+    dims = list(GRIDS.get(world, (0, 0)))
+    comm = acc.accfft_create_comm(dims, rank=rank, nprocs=world)
+    plan = acc.accfft_plan_dft_3d_r2c_gpu(n, comm)
+    isz, osz = plan.isize, plan.osize
+    n_in = isz[0] * isz[1] * isz[2]
+    gen = torch.Generator(device=dev).manual_seed(20240607 + rank)
+    x = torch.rand(max(n_in, 1), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    out = torch.zeros(max(plan.alloc_max // 8, 2), dtype=torch.float64, device=dev)
+    back = torch.zeros_like(x)
+    stream = torch.cuda.Stream()
+    plan.set_stream(stream.cuda_stream)
+    plan.set_blocking(False)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        plan.execute_r2c(x, out)
+        plan.execute_c2r(out, back)
+
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            step()
+    sync_all()
+    # correctness guard inside the bench: the round trip must reproduce the input (value is void otherwise)
+    N = n[0] * n[1] * n[2]
+    rt_err = float(torch.linalg.vector_norm(back / N - x) / torch.linalg.vector_norm(x)) if n_in else 0.0
+    if not rt_err <= 1e-12:
+        raise SystemExit("round-trip error %g exceeds 1e-12: refusing to report a number" % rt_err)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    plan.set_profiling(True)
+    plan.profile_read()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = plan.launch_count
+    sync_all()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = plan.launch_count - launches0
+    prof = plan.profile_read()
+    plan.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = 2 * flops_per_transform(n) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the public (blocking) API ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        plan.set_blocking(True)
+        xh = torch.empty(x.shape, dtype=torch.float64).pin_memory()
+        xh.copy_(x)
+        yh = torch.empty(back.shape, dtype=torch.float64).pin_memory()
+        e_steps = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            x.copy_(xh, non_blocking=True)
+            plan.execute_r2c(x, out)
+            plan.execute_c2r(out, back)
+            yh.copy_(back, non_blocking=True)
+            stream.synchronize()
+
+        with torch.cuda.stream(stream):
+            e2e_step()
+            sync_all()
+            t0 = time.perf_counter()
+            ev0.record(stream)
+            for _ in range(e_steps):
+                e2e_step()
+            ev1.record(stream)
+        sync_all()
+        e_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e_ms /= e_steps
+        ok = bool(torch.allclose(yh[:1000] / N, xh[:1000], atol=1e-12))
+        e2e = {"value": 2 * flops_per_transform(n) / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": int(xh.numel() * 8), "d2h_bytes_per_step": int(yh.numel() * 8),
+               "ms_per_step": e_ms, "steps": e_steps, "checked": ok}
+        plan.set_blocking(False)
+    clocks = sampler.result()
+
+    # ---- roofline of the dominant stage kernel -----------------------------------------------------------
+    n2c = n[2] // 2 + 1
+    k2 = osz[2]
+    R = n_in * 8
+    C0 = isz[0] * isz[1] * n2c * 16            # after Z:  [i0][i1][N2c]
+    C1 = isz[0] * n[1] * k2 * 16               # Y pass:   [i0][N1][k2]
+    C2 = n[0] * osz[1] * k2 * 16               # X pass:   [N0][k1][k2]
+    algo = {"fwd_z": R + C0, "fwd_y": C1 + C1, "fwd_x": C2 + C2, "inv_x": C2 + C2, "inv_y": C1 + C1, "inv_z": C0 + R}
+    if world > 1:      # the stage that feeds an exchange writes the NEXT layout's bytes (same totals on even grids)
+        algo["fwd_z"] = R + C0
+    peak, peak_src = measured_peaks()
+    stages = {}
+    for k, (tms, cnt) in prof.items():
+        if cnt:
+            stages[k] = {"ms": tms / cnt, "launches_per_step": cnt / args.steps}
+            if k in algo:
+                stages[k]["algo_bytes"] = algo[k]
+                stages[k]["gbs"] = algo[k] / (tms / cnt * 1e-3) / 1e9
+    dom = max((k for k in stages if k in algo), key=lambda k: stages[k]["ms"] * stages[k]["launches_per_step"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f)
+        key = "%s_n%d_p%d" % (dom, args.n, world)
+        traffic = tr.get(key)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": stages[dom]["gbs"] / peak, "traffic": traffic, "algo_bytes_per_launch": algo[dom],
+                "ms_per_launch": stages[dom]["ms"], "peak_source": peak_src}
+    # whole-step view: sum of algorithmic bytes of the six passes vs the step time
+    total_algo = sum(algo.values())
+    step_roof = {"algo_bytes_per_step": total_algo, "gbs": total_algo / (ms_per_step * 1e-3) / 1e9,
+                 "frac_of_hbm_peak": total_algo / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        from oracle import accfft_oracle as orc
+        cpu_roundtrip((64, 64, 64), cores)
+        xc = orc.cpu_input(n)
+        t_cpu = cpu_roundtrip(n, cores, xc)
+        reps = 1
+        while reps < 3 and t_cpu * (reps + 1) < 20:
+            t_cpu = min(t_cpu, cpu_roundtrip(n, cores, xc))
+            reps += 1
+        del xc
+        cpu_baseline = {"value": 2 * flops_per_transform(n) / t_cpu / 1e9, "unit": "GFLOP/s", "cores": cores,
+                        "kind": "port", "seconds_per_round_trip": t_cpu,
+                        "sample": "best of %d full %d^3 double r2c+c2r round trip(s), scipy.fft pocketfft workers=%d "
+                                  "(stand-in for FFTW+MPI, which cannot be built here)" % (reps, args.n, cores)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%d^3 double r2c+c2r round trip (forward + inverse = 1 step)" % args.n,
+                       "grid": "%dx%d" % (dims[0], dims[1]),
+                       "flops": "2 x 5 N log2 N per step", "l2": "working set %.2f GB per rank >> 126 MB L2, no flush" %
+                       ((R + 2 * C0) / 1e9), "round_trip_rel_l2": rt_err},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "stages": stages, "step_roofline": step_roof,
+        }
+        print(json.dumps(line), flush=True)
+    plan.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

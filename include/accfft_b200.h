@@ -105,6 +105,15 @@ int accfftb_plan_attach_local_peers(accfftb_plan* plan, accfftb_plan* const* pla
 int accfftb_plan_set_stream(accfftb_plan* plan, void* cuda_stream);
 int accfftb_plan_set_blocking(accfftb_plan* plan, int blocking);
 
+/* Per-launch device timing: while on, every stage / barrier kernel is bracketed by a CUDA event pair on
+ * the plan's stream (no host synchronisation).  _profile_read synchronises the stream, returns the summed
+ * milliseconds and launch counts per slot since the last read, and resets.  Slots: 0 forward Z pass,
+ * 1 forward Y, 2 forward X, 3 inverse X, 4 inverse Y, 5 inverse Z, 6 inter-GPU barrier.  (The reference
+ * only offers the coarse timer[5] of doc/timing.md.) */
+#define ACCFFTB_PROFILE_SLOTS 7
+int accfftb_plan_set_profiling(accfftb_plan* plan, int on);
+int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOTS], long long count[ACCFFTB_PROFILE_SLOTS]);
+
 long long accfftb_plan_alloc_max(const accfftb_plan* plan);
 /* number of kernels the plan has launched so far (stage kernels + inter-GPU barrier kernels) */
 long long accfftb_plan_launch_count(const accfftb_plan* plan);

@@ -425,18 +425,23 @@ def dft_definition(x: np.ndarray, sign=-1) -> np.ndarray:
 # --------------------------------------------------------------------------------------
 
 
-def cpu_roundtrip_seconds(n, dtype=np.float64, repeats=1, workers=None, c2c=False):
+def cpu_input(n, dtype=np.float64, c2c=False):
+    rng = np.random.default_rng(1)
+    if c2c:
+        return (rng.standard_normal(tuple(n)) + 1j * rng.standard_normal(tuple(n))).astype(
+            np.complex128 if dtype == np.float64 else np.complex64)
+    return rng.standard_normal(tuple(n)).astype(dtype)
+
+
+def cpu_roundtrip_seconds(n, dtype=np.float64, repeats=1, workers=None, c2c=False, x=None):
     """Time one r2c+c2r (or c2c fwd+inv) round trip with scipy.fft (pocketfft, `workers` threads).
-    Stand-in for the reference's FFTW+MPI CPU path, which cannot be built in this image."""
+    Stand-in for the reference's FFTW+MPI CPU path, which cannot be built in this image.
+    Only the two transforms are timed (input generation is outside).  Returns (best seconds, workers)."""
     import time
     import scipy.fft as sfft
     workers = workers or (os.cpu_count() or 1)
-    rng = np.random.default_rng(1)
-    if c2c:
-        x = (rng.standard_normal(tuple(n)) + 1j * rng.standard_normal(tuple(n))).astype(
-            np.complex128 if dtype == np.float64 else np.complex64)
-    else:
-        x = rng.standard_normal(tuple(n)).astype(dtype)
+    if x is None:
+        x = cpu_input(n, dtype, c2c)
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()

@@ -1,0 +1,59 @@
+"""Host-logic tests of the plan / stage-descriptor code and the kernel BODIES under the CPU fiber emulator
+(tests/emul: test infrastructure; the product never links it).  The emulator executes the same
+`stage.cuh` templates the CUDA kernels instantiate, with every rank of the process grid as an OS thread
+and peers' buffers addressed directly -- so uneven / empty pencils, the fused pack-on-store addressing and
+the barrier placement are validated here without a GPU.  Compared with the numpy oracle; tolerance
+1e-12 (double) / 1e-5 (single) relative L2 as BASELINE.json states."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import accfft_oracle as orc
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+import emul_driver as emu  # noqa: E402
+
+CASES = [((8, 8, 8), (1, 1)), ((8, 8, 8), (2, 2)), ((12, 10, 16), (2, 4)), ((6, 12, 10), (3, 2)), ((5, 6, 6), (4, 2)),
+         ((3, 5, 4), (4, 4)), ((32, 24, 20), (2, 2))]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    emu.build()
+
+
+@pytest.mark.parametrize("n,np_", CASES)
+def test_r2c_c2r_all_ranks(n, np_):
+    x = orc.synthetic_real(n, 7)
+    X = orc.forward_r2c(x)
+    w = emu.World(n, np_, r2c=True)
+    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), X) < 1e-12
+    assert orc.rel_l2(orc.assemble_output(w.forward(x, padded=True), n, np_), X) < 1e-12     # in-place layout
+    assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, np_), x * x.size) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.spectral(x, "laplace"), n, np_), orc.laplace(x)) < 1e-12
+    w.close()
+
+
+@pytest.mark.parametrize("n,np_", CASES[:5])
+def test_c2c_all_ranks(n, np_):
+    z = orc.synthetic_complex(n, 8)
+    Z = orc.forward_c2c(z)
+    w = emu.World(n, np_, r2c=False)
+    assert orc.rel_l2(orc.assemble_output(w.forward(z), n, np_, r2c=False), Z) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.inverse(Z), n, np_), z * z.size) < 1e-12
+    w.close()
+
+
+def test_single_precision():
+    n, np_ = (12, 10, 16), (2, 2)
+    x = orc.synthetic_real(n, 9)
+    w = emu.World(n, np_, r2c=True, single=True)
+    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), orc.forward_r2c(x)) < 1e-5
+    w.close()
+
+
+def test_unsupported_length_is_refused():
+    with pytest.raises(RuntimeError):
+        emu.World((7, 8, 8), (1, 1), r2c=True)
