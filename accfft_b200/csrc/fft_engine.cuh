@@ -57,6 +57,46 @@ constexpr double kS5a = 0.951056516295153572116;     // sin(2pi/5)
 constexpr double kC5b = -0.809016994374947424102;    // cos(4pi/5)
 constexpr double kS5b = 0.587785252292473129169;     // sin(4pi/5)
 
+// generic compile-time cos/sin(2 pi k / R): exact octant reduction in integers, then a Taylor series on
+// |alpha| <= pi/4 (converges to < 1 ulp in 12 terms).  Only used for the composites that have no literal above.
+constexpr double kPi4 = 0.785398163397448309615660845819875721;
+constexpr double taylor_cos(double a) {
+  double a2 = a * a, term = 1.0, sum = 1.0;
+  for (int i = 1; i <= 12; ++i) {
+    term *= -a2 / ((2.0 * i - 1.0) * (2.0 * i));
+    sum += term;
+  }
+  return sum;
+}
+constexpr double taylor_sin(double a) {
+  double a2 = a * a, term = a, sum = a;
+  for (int i = 1; i <= 12; ++i) {
+    term *= -a2 / ((2.0 * i) * (2.0 * i + 1.0));
+    sum += term;
+  }
+  return sum;
+}
+// returns cos (want_sin = false) or sin (want_sin = true) of theta = 2 pi k / R
+constexpr double generic_trig(int R, int k, bool want_sin) {
+  k = ((k % R) + R) % R;
+  const int o = (8 * k) / R;            // octant
+  const int rem = 8 * k - o * R;        // theta = (o + rem/R) * pi/4
+  int q = 0;
+  double alpha = 0.0;
+  if (o % 2 == 0) {
+    q = o / 2;
+    alpha = kPi4 * (double)rem / (double)R;
+  } else {
+    q = (o + 1) / 2;
+    alpha = -kPi4 * (double)(R - rem) / (double)R;
+  }
+  const double c = taylor_cos(alpha), sn = taylor_sin(alpha);
+  q %= 4;                               // theta = q * pi/2 + alpha
+  const double ct = q == 0 ? c : q == 1 ? -sn : q == 2 ? -c : sn;
+  const double st = q == 0 ? sn : q == 1 ? c : q == 2 ? -sn : -c;
+  return want_sin ? st : ct;
+}
+
 constexpr double root_re(int R, int k) {
   // cos(2 pi k / R) for the (R,k) pairs the composites need
   k %= R;
@@ -73,7 +113,7 @@ constexpr double root_re(int R, int k) {
   if (3 * k == R || 3 * k == 2 * R) return -0.5;
   if (12 * k == R || 12 * k == 11 * R) return kS3;
   if (12 * k == 5 * R || 12 * k == 7 * R) return -kS3;
-  return 1e300;  // unsupported -> poison (tests catch it)
+  return generic_trig(R, k, false);
 }
 constexpr double root_im(int R, int k) {
   // -sin(2 pi k / R)
@@ -91,7 +131,7 @@ constexpr double root_im(int R, int k) {
   if (3 * k == 2 * R || 6 * k == 5 * R) return kS3;
   if (12 * k == R || 12 * k == 5 * R) return -0.5;
   if (12 * k == 7 * R || 12 * k == 11 * R) return 0.5;
-  return 1e300;
+  return -generic_trig(R, k, true);
 }
 
 // multiply by the compile-time root W_R^K, using the cheap forms for multiples of 1/8 turn
@@ -207,6 +247,9 @@ template <int S, class T> struct Dft<6, S, T> : DftCT<3, 2, S, T> {};
 template <int S, class T> struct Dft<8, S, T> : DftCT<4, 2, S, T> {};
 template <int S, class T> struct Dft<12, S, T> : DftCT<3, 4, S, T> {};
 template <int S, class T> struct Dft<16, S, T> : DftCT<4, 4, S, T> {};
+template <int S, class T> struct Dft<9, S, T> : DftCT<3, 3, S, T> {};
+template <int S, class T> struct Dft<10, S, T> : DftCT<5, 2, S, T> {};
+template <int S, class T> struct Dft<15, S, T> : DftCT<5, 3, S, T> {};
 
 // ---- schedule ------------------------------------------------------------------------------------
 template <int N_, int G_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
@@ -223,6 +266,9 @@ struct Sched {
   static constexpr int regs(int p) { return cnt(p) * R[p]; }
   static constexpr int cmax(int a, int b) { return a > b ? a : b; }
   static constexpr int NREG = cmax(cmax(regs(0), NP > 1 ? regs(1) : 0), cmax(NP > 2 ? regs(2) : 0, NP > 3 ? regs(3) : 0));
+  // base twiddles a thread keeps in registers: one per (pass >= 1, butterfly slot u)
+  static constexpr int tw_off(int p) { return p <= 1 ? 0 : p == 2 ? cnt(1) : cnt(1) + cnt(2); }
+  static constexpr int NTW = NP == 1 ? 1 : NP == 2 ? cnt(1) : NP == 3 ? cnt(1) + cnt(2) : cnt(1) + cnt(2) + cnt(3);
   // shared-memory index padding: one extra slot every 8 (kills the stride-R conflicts of the
   // early scatter passes for 16-byte and 8-byte elements alike)
   static ACC_HD int phys(int i) { return i + (i >> 3); }
@@ -230,21 +276,51 @@ struct Sched {
 };
 
 // ---- per-pass building blocks ------------------------------------------------------------------------
-// tw: table W_M[k] = exp(-2 pi i k / M), k < M, with M = S::N * TWS  (TWS = 2 lets the r2c kernels share
-// the length-2M table they need for the split step).
+// Twiddles.  Butterfly j of pass P multiplies operand r by W^(r*q), q = (j % NS) * N/(NS*R).  Only the base
+// W^q is fetched from the table tw (W_M[k] = exp(-2 pi i k / M), M = S::N * TWS; TWS = 2 lets the r2c kernels
+// share the length-2M table of their split step) -- once per thread, up front, so that the fetch overlaps the
+// data loads -- and the powers are built in registers:  W^r = W^(r/2) * W^(r - r/2)  (depth <= 4 for R <= 16).
 template <class S, int P, int TWS, class T>
-ACC_HD void pass_compute(cplx<T>* v, int t, const cplx<T>* __restrict__ tw) {
+ACC_HD void load_base_twiddles_pass(cplx<T>* w1, int t, const cplx<T>* __restrict__ tw) {
+  if constexpr (P < S::NP) {
+    constexpr int R = S::radix(P), NS = S::ns(P), NB = S::nb(P), CNT = S::cnt(P);
+    constexpr int TSTEP = (S::N / (NS * R)) * TWS;
+    ACC_UNROLL
+    for (int u = 0; u < CNT; ++u) {
+      const int j = t + u * S::G;
+      w1[S::tw_off(P) + u] = (CNT * S::G == NB || j < NB) ? tw[(j % NS) * TSTEP] : cplx<T>{T(1), T(0)};
+    }
+  }
+}
+template <class S, int TWS, class T>
+ACC_HD void load_base_twiddles(cplx<T>* w1, int t, const cplx<T>* __restrict__ tw) {
+  load_base_twiddles_pass<S, 1, TWS>(w1, t, tw);
+  load_base_twiddles_pass<S, 2, TWS>(w1, t, tw);
+  load_base_twiddles_pass<S, 3, TWS>(w1, t, tw);
+}
+
+template <int R, class T>
+ACC_HD void apply_twiddle_powers(cplx<T>* v, cplx<T> w1) {
+  cplx<T> w[R > 2 ? R : 2];
+  w[1] = w1;
+  v[1] = cmul(v[1], w1);
+  ACC_UNROLL
+  for (int r = 2; r < R; ++r) {
+    const int h = r >> 1;
+    if (r == 2 * h) w[r] = {w[h].x * w[h].x - w[h].y * w[h].y, T(2) * w[h].x * w[h].y};
+    else w[r] = cmul(w[h], w[r - h]);
+    v[r] = cmul(v[r], w[r]);
+  }
+}
+
+template <class S, int P, class T>
+ACC_HD void pass_compute(cplx<T>* v, int t, const cplx<T>* w1) {
   constexpr int R = S::radix(P), NS = S::ns(P), NB = S::nb(P), CNT = S::cnt(P);
-  constexpr int TSTEP = (S::N / (NS * R)) * TWS;
   ACC_UNROLL
   for (int u = 0; u < CNT; ++u) {
     const int j = t + u * S::G;
     if (CNT * S::G == NB || j < NB) {
-      if constexpr (NS > 1) {
-        const int q = (j % NS) * TSTEP;
-        ACC_UNROLL
-        for (int r = 1; r < R; ++r) v[u * R + r] = cmul(v[u * R + r], tw[r * q]);
-      }
+      if constexpr (NS > 1) apply_twiddle_powers<R, T>(v + u * R, w1[S::tw_off(P) + u]);
       Dft<R, 1, T>::run(v + u * R);
     }
   }
@@ -295,29 +371,30 @@ ACC_HD void pass_foreach(cplx<T>* v, int t, F f) {
 
 // Run passes 0..NP-1 on registers already holding pass-0 operands (gather order); on return the
 // registers hold the final outputs in pass-(NP-1) gather order (index j + r*N/R_last).
-// smem_addr(i) -> pointer to this column's slot i;  sync() is a CTA-wide barrier.
-template <class S, int TWS, class T, class Addr, class Sync>
-ACC_HD void fft_passes(cplx<T>* v, int t, const cplx<T>* __restrict__ tw, Addr smem_addr, Sync sync) {
-  pass_compute<S, 0, TWS>(v, t, tw);
+// w1: base twiddles from load_base_twiddles.  smem_addr(i) -> pointer to this column's slot i;
+// sync() is a CTA-wide barrier.
+template <class S, class T, class Addr, class Sync>
+ACC_HD void fft_passes(cplx<T>* v, int t, const cplx<T>* w1, Addr smem_addr, Sync sync) {
+  pass_compute<S, 0>(v, t, w1);
   if constexpr (S::NP > 1) {
     pass_scatter<S, 0>(v, t, smem_addr);
     sync();
     pass_gather<S, 1>(v, t, smem_addr);
-    pass_compute<S, 1, TWS>(v, t, tw);
+    pass_compute<S, 1>(v, t, w1);
   }
   if constexpr (S::NP > 2) {
     sync();
     pass_scatter<S, 1>(v, t, smem_addr);
     sync();
     pass_gather<S, 2>(v, t, smem_addr);
-    pass_compute<S, 2, TWS>(v, t, tw);
+    pass_compute<S, 2>(v, t, w1);
   }
   if constexpr (S::NP > 3) {
     sync();
     pass_scatter<S, 2>(v, t, smem_addr);
     sync();
     pass_gather<S, 3>(v, t, smem_addr);
-    pass_compute<S, 3, TWS>(v, t, tw);
+    pass_compute<S, 3>(v, t, w1);
   }
 }
 

@@ -18,15 +18,15 @@ struct CudaCtx {
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 
-template <class T, class S, bool INV>
+template <class T, class S>
 __global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS) k_strided_c2c(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  strided_c2c_body<T, S, Cfg<T, S>::TC, INV>(d, ctx);
+  strided_c2c_body<T, S, Cfg<T, S>::TC>(d, ctx);
 }
-template <class T, class S, bool INV>
+template <class T, class S>
 __global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_c2c(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  contig_c2c_body<T, S, Cfg<T, S>::PC, INV>(d, ctx);
+  contig_c2c_body<T, S, Cfg<T, S>::PC>(d, ctx);
 }
 template <class T, class S>
 __global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_r2c(const __grid_constant__ StageDesc d) {
@@ -57,12 +57,10 @@ static int launch_one(const Launch& l, cudaStream_t st) {
   const StageDesc& d = l.desc;
 #if ACCFFT_KIND == 0
   const long long nb = (long long)d.nA * ((d.nB + C::TC - 1) / C::TC);
-  if (l.inverse) return launch_kernel(k_strided_c2c<T, S, true>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st);
-  return launch_kernel(k_strided_c2c<T, S, false>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st);
+  return launch_kernel(k_strided_c2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st);
 #elif ACCFFT_KIND == 1
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-  if (l.inverse) return launch_kernel(k_contig_c2c<T, S, true>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st);
-  return launch_kernel(k_contig_c2c<T, S, false>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st);
+  return launch_kernel(k_contig_c2c<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st);
 #elif ACCFFT_KIND == 2
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
   return launch_kernel(k_contig_r2c<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st);

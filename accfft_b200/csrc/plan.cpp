@@ -79,6 +79,7 @@ Launch Plan::fwd_z(const void* in, bool in_padded) const {
   l.inverse = false;
   l.desc = d;
   l.slot = 0;
+  l.desc.inv = l.inverse ? 1 : 0;
   return l;
 }
 
@@ -110,6 +111,7 @@ Launch Plan::fwd_y() const {
   l.inverse = false;
   l.desc = d;
   l.slot = 1;
+  l.desc.inv = l.inverse ? 1 : 0;
   return l;
 }
 
@@ -147,6 +149,7 @@ Launch Plan::fwd_x(void* out) const {
   l.inverse = false;
   l.desc = d;
   l.slot = 2;
+  l.desc.inv = l.inverse ? 1 : 0;
   return l;
 }
 
@@ -177,6 +180,7 @@ Launch Plan::inv_x(const void* in) const {
   l.inverse = true;
   l.desc = d;
   l.slot = 3;
+  l.desc.inv = l.inverse ? 1 : 0;
   return l;
 }
 
@@ -208,6 +212,7 @@ Launch Plan::inv_y() const {
   l.inverse = true;
   l.desc = d;
   l.slot = 4;
+  l.desc.inv = l.inverse ? 1 : 0;
   return l;
 }
 
@@ -242,6 +247,7 @@ Launch Plan::inv_z(void* out, bool out_padded) const {
   l.inverse = true;
   l.desc = d;
   l.slot = 5;
+  l.desc.inv = l.inverse ? 1 : 0;
   return l;
 }
 

@@ -52,6 +52,7 @@ struct StageDesc {
   double scale;
   int opOnLoad;          // 1: apply `op` to the INPUT elements (inverse X stage of grad) instead of the outputs
   int accumulate;        // 1: outputs are added to the destination (divergence sums three spectra)
+  int inv;               // 1: inverse transform (sign +1), done as swap(re,im) . forward . swap(re,im)
 };
 
 template <class T>
@@ -104,13 +105,32 @@ ACC_HD cplx<T> apply_op(const StageDesc& d, cplx<T> v, int k, int a, int b) {
   return {T(w * v.x), T(w * v.y)};
 }
 
+// true when the stage needs none of the generic machinery: one destination segment, no spectral operator
+ACC_HD bool stage_is_simple(const StageDesc& d) { return d.nseg == 1 && d.op == OP_NONE && d.accumulate == 0; }
+
+template <class T>
+ACC_HD cplx<T> cswap_if(cplx<T> a, bool sw) { return sw ? cplx<T>{a.y, a.x} : a; }
+
+// generic (segmented / operator) store of output element k of column (a, b)
+template <class T>
+ACC_HD void store_generic(const StageDesc& d, cplx<T> y, int k, int a, int b) {
+  const int s = seg_of(d, k);
+  const SegDst& sd = d.seg[s];
+  cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB +
+                 (long long)(k - s * d.blk) * sd.strideI;
+  store_out(d, dst, d.opOnLoad ? y : apply_op(d, y, k, a, b));
+}
+
 // ================================================================================================
 // strided c2c: transform index strided in memory, TC adjacent columns (unit stride) per CTA tile.
 // Used for the Y and X passes (reference: fplan_1 / fplan_2, src/accfft_gpu.cpp:208-253).
 // threads = S::G * TC;  tid -> (c = tid % TC, t = tid / TC);  smem layout [phys(i)][c]
 // ================================================================================================
-template <class T, class S, int TC, bool INV, class Ctx>
+template <class T, class S, int TC, class Ctx>
 ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
+  constexpr int G = S::G;
+  constexpr int R0 = S::radix(0), NB0 = S::nb(0), CNT0 = S::cnt(0);
+  constexpr int RL = S::radix(S::NP - 1), NBL = S::nb(S::NP - 1), CNTL = S::cnt(S::NP - 1);
   const int tid = ctx.tid();
   const int c = tid % TC, t = tid / TC;
   const int tpa = (d.nB + TC - 1) / TC;
@@ -118,30 +138,56 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
   const int a = (int)(tile / tpa);
   const int b = (int)(tile % tpa) * TC + c;
   const bool valid = b < d.nB;
+  const bool inv = d.inv != 0;
+  const bool simple = stage_is_simple(d);
+  cplx<T> w1[S::NTW];
+  load_base_twiddles<S, 1>(w1, t, (const cplx<T>*)d.tw);
   cplx<T> v[S::NREG];
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
   if (valid) {
     const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + b;
     const long long si = d.inStrideI;
-    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) {
-      cplx<T> x = in[(long long)i * si];
-      if (d.opOnLoad) x = apply_op(d, x, i, a, b);
-      r = INV ? cswap(x) : x;
-    });
+    const long long step = (long long)NB0 * si;
+    ACC_UNROLL
+    for (int u = 0; u < CNT0; ++u) {
+      const int j = t + u * G;
+      if (CNT0 * G == NB0 || j < NB0) {
+        const cplx<T>* p = in + (long long)j * si;
+        ACC_UNROLL
+        for (int r = 0; r < R0; ++r) v[u * R0 + r] = p[r * step];
+      }
+    }
+    if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = apply_op(d, r, i, a, b); });
+    if (inv) {
+      ACC_UNROLL
+      for (int i = 0; i < S::NREG; ++i) v[i] = cswap(v[i]);
+    }
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem();
-  fft_passes<S, 1>(v, t, (const cplx<T>*)d.tw, [&](int i) { return sm + S::phys(i) * TC + c; },
-                   [&]() { ctx.sync(); });
+  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i) * TC + c; }, [&]() { ctx.sync(); });
   if (valid) {
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) {
-      const int s = seg_of(d, k);
-      const SegDst& sd = d.seg[s];
-      cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB +
-                     (long long)(k - s * d.blk) * sd.strideI;
-      cplx<T> y = INV ? cswap(r) : r;
-      store_out(d, dst, d.opOnLoad ? y : apply_op(d, y, k, a, b));
-    });
+    if (inv) {
+      ACC_UNROLL
+      for (int i = 0; i < S::NREG; ++i) v[i] = cswap(v[i]);
+    }
+    if (simple) {
+      const SegDst& sd = d.seg[0];
+      cplx<T>* out = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
+      const long long so = sd.strideI;
+      const long long step = (long long)NBL * so;
+      ACC_UNROLL
+      for (int u = 0; u < CNTL; ++u) {
+        const int j = t + u * G;
+        if (CNTL * G == NBL || j < NBL) {
+          cplx<T>* p = out + (long long)j * so;
+          ACC_UNROLL
+          for (int r = 0; r < RL; ++r) p[r * step] = v[u * RL + r];
+        }
+      }
+    } else {
+      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, r, k, a, b); });
+    }
   }
 }
 
@@ -149,7 +195,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
 // contiguous c2c: transform index has unit stride; PC pencils per CTA, G threads per pencil.
 // Used for the Z pass of c2c plans (reference fplan_0 of the c2c plan, src/accfft_gpu.cpp:767-790).
 // ================================================================================================
-template <class T, class S, int PC, bool INV, class Ctx>
+template <class T, class S, int PC, class Ctx>
 ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
   const int tid = ctx.tid();
   const int t = tid % S::G, pcl = tid / S::G;
@@ -157,27 +203,27 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
   const bool valid = idx < (long long)d.nA * d.nB;
   const int a = valid ? (int)(idx / d.nB) : 0;
   const int b = valid ? (int)(idx % d.nB) : 0;
+  const bool inv = d.inv != 0;
+  cplx<T> w1[S::NTW];
+  load_base_twiddles<S, 1>(w1, t, (const cplx<T>*)d.tw);
   cplx<T> v[S::NREG];
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
   if (valid) {
     const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB;
-    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) {
-      cplx<T> x = in[i];
-      r = INV ? cswap(x) : x;
-    });
+    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = cswap_if(in[i], inv); });
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
-  fft_passes<S, 1>(v, t, (const cplx<T>*)d.tw, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
   if (valid) {
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) {
-      const int s = seg_of(d, k);
-      const SegDst& sd = d.seg[s];
-      cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB +
-                     (long long)(k - s * d.blk) * sd.strideI;
-      cplx<T> y = INV ? cswap(r) : r;
-      *dst = apply_op(d, y, k, a, b);
-    });
+    if (stage_is_simple(d)) {
+      const SegDst& sd = d.seg[0];
+      cplx<T>* out = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
+      const long long so = sd.strideI;
+      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { out[(long long)k * so] = cswap_if(r, inv); });
+    } else {
+      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, cswap_if(r, inv), k, a, b); });
+    }
   }
 }
 
@@ -196,6 +242,9 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   const bool valid = idx < (long long)d.nA * d.nB;
   const int a = valid ? (int)(idx / d.nB) : 0;
   const int b = valid ? (int)(idx % d.nB) : 0;
+  const cplx<T>* tw = (const cplx<T>*)d.tw;
+  cplx<T> w1[S::NTW];
+  load_base_twiddles<S, 2>(w1, t, tw);
   cplx<T> v[S::NREG];
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
@@ -204,21 +253,21 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
     pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = in[i]; });
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
-  const cplx<T>* tw = (const cplx<T>*)d.tw;
-  fft_passes<S, 2>(v, t, tw, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
   // publish Z so every thread can read its mirror partner Z[M-k]
   if constexpr (S::NP > 1) ctx.sync();
   pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { sm[S::phys(k)] = r; });
   ctx.sync();
   if (valid) {
+    const bool simple = stage_is_simple(d);
+    const SegDst& s0 = d.seg[0];
+    cplx<T>* out0 = (cplx<T>*)s0.base + (long long)a * s0.strideA + (long long)b * s0.strideB;
+    const long long so = s0.strideI;
+    auto put = [&](int kk, cplx<T> y) {
+      if (simple) out0[(long long)kk * so] = y;
+      else store_generic(d, y, kk, a, b);
+    };
     pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& z) {
-      auto put = [&](int kk, cplx<T> y) {
-        const int s = seg_of(d, kk);
-        const SegDst& sd = d.seg[s];
-        cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB +
-                       (long long)(kk - s * d.blk) * sd.strideI;
-        *dst = apply_op(d, y, kk, a, b);
-      };
       if (k == 0) {
         put(0, cplx<T>{z.x + z.y, T(0)});
         put(M, cplx<T>{z.x - z.y, T(0)});
@@ -251,9 +300,15 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
   const int b = valid ? (int)(idx % d.nB) : 0;
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   const cplx<T>* tw = (const cplx<T>*)d.tw;
+  cplx<T> w1[S::NTW];
+  load_base_twiddles<S, 2>(w1, t, tw);
   if (valid) {
     const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB;
-    for (int i = t; i <= M; i += S::G) sm[S::phys(i)] = apply_op(d, in[i], i, a, b);
+    if (d.op == OP_NONE) {
+      for (int i = t; i <= M; i += S::G) sm[S::phys(i)] = in[i];
+    } else {
+      for (int i = t; i <= M; i += S::G) sm[S::phys(i)] = apply_op(d, in[i], i, a, b);
+    }
   } else {
     for (int i = t; i <= M; i += S::G) sm[S::phys(i)] = {T(0), T(0)};
   }
@@ -278,7 +333,7 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
     r = cswap(z);   // inverse transform = swap . forward . swap
   });
   ctx.sync();
-  fft_passes<S, 2>(v, t, tw, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
   if (valid) {
     const SegDst& sd = d.seg[0];
     cplx<T>* out = (cplx<T>*)((T*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB);

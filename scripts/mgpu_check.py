@@ -1,0 +1,114 @@
+"""Multi-GPU parity + timing check, one process per GPU:
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/mgpu_check.py
+Compares every rank's block with the numpy oracle (rank 0 generates the global field from a seed; every rank
+regenerates it locally -- no data collective is needed for the check)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+import accfft_b200 as acc
+from oracle import accfft_oracle as orc
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+GRIDS = {2: [(2, 1), (1, 2)], 4: [(2, 2), (1, 4), (4, 1)], 8: [(2, 4), (4, 2), (8, 1)]}[world]
+worst = 0.0
+
+
+def check(n, dims, r2c, single=False):
+    global worst
+    comm = acc.accfft_create_comm(list(dims))
+    p = acc.Plan(n, comm, r2c=r2c, single=single)
+    rdt, cdt = (np.float32, np.complex64) if single else (np.float64, np.complex128)
+    x = orc.synthetic_real(n, 5) if r2c else orc.synthetic_complex(n, 5)
+    X = orc.forward_r2c(x) if r2c else orc.forward_c2c(x)
+    loc = orc.local_input(x, n, dims, comm.coords).astype(rdt if r2c else cdt)
+    xd = torch.from_numpy(np.ascontiguousarray(loc)).to(dev) if loc.size else torch.zeros(2, dtype=torch.float64, device=dev)
+    es = 4 if single else 8
+    out = torch.zeros(max(p.alloc_max // es, 2), dtype=torch.float32 if single else torch.float64, device=dev)
+    back = torch.zeros_like(xd)
+    errs = []
+    for it in range(2):
+        if r2c:
+            p.execute_r2c(xd, out); p.execute_c2r(out, back)
+        else:
+            p.execute_c2c(acc.ACCFFT_FORWARD, xd, out); p.execute_c2c(acc.ACCFFT_BACKWARD, out, back)
+    osz = p.osize
+    cnt = osz[0] * osz[1] * osz[2]
+    want = orc.local_output(X, n, dims, comm.coords, r2c=r2c)
+    if cnt:
+        got = out.cpu().numpy().view(cdt)[:cnt].reshape(osz)
+        errs.append(orc.rel_l2(got, want))
+    if loc.size:
+        errs.append(orc.rel_l2(back.cpu().numpy().reshape(loc.shape) / x.size, loc))
+    if r2c and loc.size:
+        la = torch.zeros_like(xd)
+        p.laplace(la, xd)
+        errs.append(orc.rel_l2(la.cpu().numpy().reshape(loc.shape), orc.local_input(orc.laplace(x), n, dims, comm.coords)))
+        g = [torch.zeros_like(xd) for _ in range(3)]
+        p.grad(g[0], g[1], g[2], xd)
+        for ax in range(3):
+            errs.append(orc.rel_l2(g[ax].cpu().numpy().reshape(loc.shape), orc.local_input(orc.grad(x, ax), n, dims, comm.coords)))
+    elif r2c:
+        la = torch.zeros_like(xd); p.laplace(la, xd)
+        g = [torch.zeros_like(xd) for _ in range(3)]; p.grad(g[0], g[1], g[2], xd)
+    e = max(errs) if errs else 0.0
+    t = torch.tensor([e], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    worst = max(worst, float(t.item()) / (1e7 if single else 1.0))
+    if rank == 0:
+        print(f"n={n} dims={dims} r2c={r2c} single={single}: max rel-L2 over ranks {float(t.item()):.2e}", flush=True)
+    p.destroy()
+
+
+for dims in GRIDS:
+    for n in [(16, 12, 20), (64, 64, 64), (48, 40, 36), (5, 6, 6), (128, 96, 160)]:
+        check(n, dims, True)
+        check(n, dims, False)
+    check((64, 64, 64), dims, True, single=True)
+
+
+def bench(n, dims, r2c=True, iters=20):
+    comm = acc.accfft_create_comm(list(dims))
+    p = acc.Plan(n, comm, r2c=r2c, single=False)
+    isz = p.isize
+    cnt = isz[0] * isz[1] * isz[2] * (1 if r2c else 2)
+    x = torch.rand(cnt, dtype=torch.float64, device=dev)
+    out = torch.zeros(p.alloc_max // 8, dtype=torch.float64, device=dev)
+    back = torch.zeros_like(x)
+    st = torch.cuda.Stream()
+    p.set_stream(st.cuda_stream); p.set_blocking(False); p.set_profiling(True)
+    def step():
+        if r2c:
+            p.execute_r2c(x, out); p.execute_c2r(out, back)
+        else:
+            p.execute_c2c(acc.ACCFFT_FORWARD, x, out); p.execute_c2c(acc.ACCFFT_BACKWARD, out, back)
+    with torch.cuda.stream(st):
+        for _ in range(3): step()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize(); p.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        e0.record(st)
+        for _ in range(iters): step()
+        e1.record(st)
+    torch.cuda.synchronize(); dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    prof = p.profile_read()
+    N = n[0] * n[1] * n[2]
+    gf = 2 * 5 * N * np.log2(N) / (float(ms.item()) * 1e-3) / 1e9
+    if rank == 0:
+        print(f"bench n={n} dims={dims} r2c={r2c}: {float(ms.item()):.3f} ms/round-trip  {gf:.0f} GFLOP/s  stages(ms/launch): " +
+              " ".join(f"{k}={v[0]/max(v[1],1):.3f}" for k, v in prof.items()), flush=True)
+    p.destroy()
+
+
+for dims in GRIDS[:2]:
+    bench((512, 512, 512), dims, True)
+    bench((512, 512, 512), dims, False)
+if rank == 0:
+    print("WORST", worst, "PASS" if worst <= 1e-12 else "FAIL", flush=True)
+dist.destroy_process_group()

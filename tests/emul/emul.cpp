@@ -113,18 +113,12 @@ static void emu_launch_sched(const Launch& l) {
   switch (l.kind) {
     case K_STRIDED_C2C: {
       const long long nb = (long long)d.nA * ((d.nB + C::TC - 1) / C::TC);
-      if (l.inverse)
-        run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) { strided_c2c_body<T, S, C::TC, true>(d, c); });
-      else
-        run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) { strided_c2c_body<T, S, C::TC, false>(d, c); });
+      run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) { strided_c2c_body<T, S, C::TC>(d, c); });
       break;
     }
     case K_CONTIG_C2C: {
       const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-      if (l.inverse)
-        run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2c_body<T, S, C::PC, true>(d, c); });
-      else
-        run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2c_body<T, S, C::PC, false>(d, c); });
+      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2c_body<T, S, C::PC>(d, c); });
       break;
     }
     case K_CONTIG_R2C: {

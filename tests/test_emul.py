@@ -16,7 +16,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu
 import emul_driver as emu  # noqa: E402
 
 CASES = [((8, 8, 8), (1, 1)), ((8, 8, 8), (2, 2)), ((12, 10, 16), (2, 4)), ((6, 12, 10), (3, 2)), ((5, 6, 6), (4, 2)),
-         ((3, 5, 4), (4, 4)), ((32, 24, 20), (2, 2))]
+         ((3, 5, 4), (4, 4)), ((32, 24, 20), (2, 2)), ((18, 30, 50), (1, 2)), ((45, 15, 90), (2, 1)), ((9, 10, 2), (1, 1)),
+         ((75, 4, 36), (1, 1))]
 
 
 @pytest.fixture(scope="module", autouse=True)
