@@ -15,6 +15,7 @@
 
 #include "../../include/accfft_b200.h"
 #include "plan.hpp"
+#include "kernel_cfg.hpp"
 
 namespace accfft_b200 {
 
@@ -46,7 +47,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 static bool length_supported(int N) {
 #define X(N_, G_, R0, R1, R2, R3) \
   if (N == N_) return true;
-#include "schedules.def"
+#include ACCFFT_SCHEDULES_FILE
 #undef X
   return false;
 }

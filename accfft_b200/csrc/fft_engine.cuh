@@ -14,6 +14,7 @@
 // only the exchanges between passes go through shared memory.
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 
 #if defined(__CUDACC__)
 #define ACC_HD __host__ __device__ __forceinline__
@@ -250,6 +251,15 @@ template <int S, class T> struct Dft<16, S, T> : DftCT<4, 4, S, T> {};
 template <int S, class T> struct Dft<9, S, T> : DftCT<3, 3, S, T> {};
 template <int S, class T> struct Dft<10, S, T> : DftCT<5, 2, S, T> {};
 template <int S, class T> struct Dft<15, S, T> : DftCT<5, 3, S, T> {};
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
+template <int B, int E, class F>
+ACC_HD void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
 
 // ---- schedule ------------------------------------------------------------------------------------
 template <int N_, int G_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>

@@ -2,10 +2,17 @@
 #pragma once
 #include "fft_engine.cuh"
 
+#ifndef ACCFFT_SCHEDULES_FILE
+#define ACCFFT_SCHEDULES_FILE "schedules.def"
+#endif
+
 namespace accfft_b200 {
 
 #ifndef ACCFFT_MAX_STRIDED_THREADS
 #define ACCFFT_MAX_STRIDED_THREADS 512
+#endif
+#ifndef ACCFFT_CONTIG_THREADS
+#define ACCFFT_CONTIG_THREADS 128
 #endif
 #ifndef ACCFFT_MAX_STRIDED_SMEM
 #define ACCFFT_MAX_STRIDED_SMEM (100 * 1024)
@@ -24,8 +31,8 @@ struct Cfg {
   static constexpr int TC = tc_pick();
   static constexpr int STRIDED_THREADS = S::G * TC;
   static constexpr int STRIDED_SMEM = S::SMEM_ELEMS * TC * (int)sizeof(cplx<T>);
-  // contiguous kernels: PC pencils per CTA, about 128 threads
-  static constexpr int PC = (S::G >= 128) ? 1 : 128 / S::G;
+  // contiguous kernels: PC pencils per CTA, about ACCFFT_CONTIG_THREADS threads
+  static constexpr int PC = (S::G >= ACCFFT_CONTIG_THREADS) ? 1 : ACCFFT_CONTIG_THREADS / S::G;
   static constexpr int CONTIG_THREADS = S::G * PC;
   static constexpr int CONTIG_SMEM = S::SMEM_ELEMS * PC * (int)sizeof(cplx<T>);
 };

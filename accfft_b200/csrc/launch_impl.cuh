@@ -74,7 +74,7 @@ template <class T>
 static int launch_any(const Launch& l, cudaStream_t st) {
 #define X(N_, G_, R0, R1, R2, R3) \
   if (l.fftN == N_) return launch_one<T, Sched<N_, G_, R0, R1, R2, R3>>(l, st);
-#include "schedules.def"
+#include ACCFFT_SCHEDULES_FILE
 #undef X
   return -1;
 }

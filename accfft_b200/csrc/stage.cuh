@@ -245,6 +245,9 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   const cplx<T>* tw = (const cplx<T>*)d.tw;
   cplx<T> w1[S::NTW];
   load_base_twiddles<S, 2>(w1, t, tw);
+  cplx<T> ws[S::cnt(S::NP - 1)];
+  ACC_UNROLL
+  for (int u = 0; u < S::cnt(S::NP - 1); ++u) ws[u] = tw[(t + u * S::G) % M];
   cplx<T> v[S::NREG];
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
@@ -259,6 +262,7 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { sm[S::phys(k)] = r; });
   ctx.sync();
   if (valid) {
+    constexpr int RL = S::radix(S::NP - 1), NBL = S::nb(S::NP - 1), CNTL = S::cnt(S::NP - 1);
     const bool simple = stage_is_simple(d);
     const SegDst& s0 = d.seg[0];
     cplx<T>* out0 = (cplx<T>*)s0.base + (long long)a * s0.strideA + (long long)b * s0.strideB;
@@ -267,19 +271,30 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
       if (simple) out0[(long long)kk * so] = y;
       else store_generic(d, y, kk, a, b);
     };
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& z) {
-      if (k == 0) {
-        put(0, cplx<T>{z.x + z.y, T(0)});
-        put(M, cplx<T>{z.x - z.y, T(0)});
-      } else {
-        const cplx<T> p = sm[S::phys(M - k)];
-        const cplx<T> w = tw[k];
-        const cplx<T> e = {z.x + p.x, z.y - p.y};      // Z[k] + conj(Z[M-k])
-        const cplx<T> o = {z.y + p.y, p.x - z.x};      // -i * (Z[k] - conj(Z[M-k]))
-        const cplx<T> wo = cmul(w, o);
-        put(k, cplx<T>{T(0.5) * (e.x + wo.x), T(0.5) * (e.y + wo.y)});
+    // split step X[k] = (E + W_N2^k O)/2 for k = j + r*NBL:  W_N2^k = W_N2^j * W_(2 RL)^r, the second factor a
+    // compile-time root, so only ws[u] = W_N2^j comes from the table (fetched up front)
+    ACC_UNROLL
+    for (int u = 0; u < CNTL; ++u) {
+      const int j = t + u * S::G;
+      if (CNTL * S::G == NBL || j < NBL) {
+        const cplx<T> wj = ws[u];
+        static_for<0, RL>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          const int k = j + r * NBL;
+          const cplx<T> z = v[u * RL + r];
+          if (r == 0 && k == 0) {
+            put(0, cplx<T>{z.x + z.y, T(0)});
+            put(M, cplx<T>{z.x - z.y, T(0)});
+          } else {
+            const cplx<T> p = sm[S::phys(M - k)];
+            const cplx<T> e = {z.x + p.x, z.y - p.y};                       // Z[k] + conj(Z[M-k])
+            const cplx<T> o = mul_root<2 * RL, r, T>(cplx<T>{z.y + p.y, p.x - z.x});   // -i (Z[k] - conj(Z[M-k])) * W_(2RL)^r
+            const cplx<T> wo = cmul(wj, o);
+            put(k, cplx<T>{T(0.5) * (e.x + wo.x), T(0.5) * (e.y + wo.y)});
+          }
+        });
       }
-    });
+    }
   }
 }
 
@@ -300,38 +315,69 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
   const int b = valid ? (int)(idx % d.nB) : 0;
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   const cplx<T>* tw = (const cplx<T>*)d.tw;
+  constexpr int R0 = S::radix(0), NB0 = S::nb(0), CNT0 = S::cnt(0);
   cplx<T> w1[S::NTW];
   load_base_twiddles<S, 2>(w1, t, tw);
-  if (valid) {
-    const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB;
-    if (d.op == OP_NONE) {
-      for (int i = t; i <= M; i += S::G) sm[S::phys(i)] = in[i];
-    } else {
-      for (int i = t; i <= M; i += S::G) sm[S::phys(i)] = apply_op(d, in[i], i, a, b);
+  cplx<T> ws[CNT0];
+  ACC_UNROLL
+  for (int u = 0; u < CNT0; ++u) ws[u] = tw[(t + u * S::G) % M];
+  {
+    // stage the M+1 input coefficients in shared memory (all global loads issued before the first use)
+    constexpr int NLD = (M + 1 + S::G - 1) / S::G;
+    cplx<T> x[NLD];
+    ACC_UNROLL
+    for (int q = 0; q < NLD; ++q) x[q] = {T(0), T(0)};
+    if (valid) {
+      const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB;
+      ACC_UNROLL
+      for (int q = 0; q < NLD; ++q) {
+        const int i = t + q * S::G;
+        if (i <= M) x[q] = in[i];
+      }
+      if (d.op != OP_NONE) {
+        ACC_UNROLL
+        for (int q = 0; q < NLD; ++q) {
+          const int i = t + q * S::G;
+          if (i <= M) x[q] = apply_op(d, x[q], i, a, b);
+        }
+      }
     }
-  } else {
-    for (int i = t; i <= M; i += S::G) sm[S::phys(i)] = {T(0), T(0)};
+    ACC_UNROLL
+    for (int q = 0; q < NLD; ++q) {
+      const int i = t + q * S::G;
+      if (i <= M) sm[S::phys(i)] = x[q];
+    }
   }
   ctx.sync();
   cplx<T> v[S::NREG];
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
-  pass_foreach<S, 0>(v, t, [&](int k, cplx<T>& r) {
-    const cplx<T> A = sm[S::phys(k)];
-    const cplx<T> B = sm[S::phys(M - k)];
-    cplx<T> z;
-    if (k == 0) {
-      z = {A.x + B.x, A.x - B.x};
-    } else {
-      const cplx<T> w = tw[k];
-      const cplx<T> e = {A.x + B.x, A.y - B.y};   // X[k] + conj(X[M-k])
-      const cplx<T> D = {A.x - B.x, A.y + B.y};   // X[k] - conj(X[M-k])
-      // i * conj(w) * D
-      const cplx<T> q = {-(w.x * D.y - w.y * D.x), w.x * D.x + w.y * D.y};
-      z = cadd(e, q);
+  // Z'[k] = (X[k] + conj(X[M-k])) + i conj(W_N2^k) (X[k] - conj(X[M-k])) for k = j + r*NB0, with
+  // W_N2^k = W_N2^j * W_(2 R0)^r (compile-time second factor)
+  ACC_UNROLL
+  for (int u = 0; u < CNT0; ++u) {
+    const int j = t + u * S::G;
+    if (CNT0 * S::G == NB0 || j < NB0) {
+      const cplx<T> wj = ws[u];
+      static_for<0, R0>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        const int k = j + r * NB0;
+        const cplx<T> A = sm[S::phys(k)];
+        const cplx<T> B = sm[S::phys(M - k)];
+        cplx<T> z;
+        if (r == 0 && k == 0) {
+          z = {A.x + B.x, A.x - B.x};
+        } else {
+          const cplx<T> e = {A.x + B.x, A.y - B.y};                             // X[k] + conj(X[M-k])
+          const cplx<T> D = mul_root<2 * R0, -r, T>(cplx<T>{A.x - B.x, A.y + B.y});   // (X[k] - conj(X[M-k])) conj(W_(2R0)^r)
+          // i * conj(wj) * D
+          const cplx<T> q = {-(wj.x * D.y - wj.y * D.x), wj.x * D.x + wj.y * D.y};
+          z = cadd(e, q);
+        }
+        v[u * R0 + r] = cswap(z);   // inverse transform = swap . forward . swap
+      });
     }
-    r = cswap(z);   // inverse transform = swap . forward . swap
-  });
+  }
   ctx.sync();
   fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
   if (valid) {

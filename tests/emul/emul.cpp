@@ -140,7 +140,7 @@ static void emu_launch_sched(const Launch& l) {
 static bool emu_supported(int N) {
 #define X(N_, G_, R0, R1, R2, R3) \
   if (N == N_) return true;
-#include "../../accfft_b200/csrc/schedules.def"
+#include ACCFFT_SCHEDULES_FILE
 #undef X
   return false;
 }
@@ -152,7 +152,7 @@ static void emu_launch(const Launch& l) {
     else emu_launch_sched<float, Sched<N_, G_, R0, R1, R2, R3>>(l);                        \
     return;                                                                             \
   }
-#include "../../accfft_b200/csrc/schedules.def"
+#include ACCFFT_SCHEDULES_FILE
 #undef X
   fprintf(stderr, "emul: no schedule for N=%d\n", l.fftN);
   abort();

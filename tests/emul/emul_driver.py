@@ -25,7 +25,8 @@ def build(force=False):
         m = os.path.getmtime(LIB)
         if all(os.path.getmtime(p) <= m for p in SOURCES + HEADERS):
             return LIB
-    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unused-function", *SOURCES, "-o", LIB,
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unused-function",
+           "-I", os.path.join(ROOT, "accfft_b200", "csrc"), *SOURCES, "-o", LIB,
            "-lpthread"]
     subprocess.check_call(cmd)
     return LIB

@@ -223,7 +223,9 @@ def test_step5_operators_closed_form_256(cuda_device):
     assert l1(o[1].cpu().numpy(), t["gy"]) < 1e-10
     assert l1(o[2].cpu().numpy(), t["gz"]) < 1e-10
     assert l1(o[3].cpu().numpy(), t["laplace"]) < 1e-10
-    assert l1(o[4].cpu().numpy(), t["biharmonic"]) < 1e-9
+    # |k|^4 amplifies rounding: the float64 oracle itself is 3.9e-9 away from the closed form at 256^3
+    assert l1(o[4].cpu().numpy(), t["biharmonic"]) < 2e-8
+    assert orc.rel_l2(o[4].cpu().numpy(), orc.biharmonic(t["f"])) < 1e-10
     assert l1(o[5].cpu().numpy(), t["laplace"]) < 1e-10
     p.destroy()
 
