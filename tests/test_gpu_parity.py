@@ -225,7 +225,8 @@ def test_step5_operators_closed_form_256(cuda_device):
     assert l1(o[3].cpu().numpy(), t["laplace"]) < 1e-10
     # |k|^4 amplifies rounding: the float64 oracle itself is 3.9e-9 away from the closed form at 256^3
     assert l1(o[4].cpu().numpy(), t["biharmonic"]) < 2e-8
-    assert orc.rel_l2(o[4].cpu().numpy(), orc.biharmonic(t["f"])) < 1e-10
+    # two correct double-precision FFTs differ by rounding noise that |k|^4 (up to 2.4e9 here) amplifies
+    assert orc.rel_l2(o[4].cpu().numpy(), orc.biharmonic(t["f"])) < 5e-9
     assert l1(o[5].cpu().numpy(), t["laplace"]) < 1e-10
     p.destroy()
 
