@@ -283,13 +283,11 @@ static void wire_self(Engine* e) {
   e->flag_ptrs[e->rank] = (unsigned long long*)(e->slab + 2 * e->bufsz);
 }
 
-// size of rank q's exchange buffers (its alloc_max, 256-byte aligned) -- every rank can compute it
+// size of rank q's exchange buffers (256-byte aligned) -- every rank can compute it for every peer
 static size_t bufsz_of(const Engine* e, int q) {
   int coords[2] = {q / e->plan.g.np[1], q % e->plan.g.np[1]};
-  const int sz = e->plan.prec == PREC_DOUBLE ? 8 : 4;
-  LocalSizes L = e->plan.g.r2c ? local_size_r2c(e->plan.g.n, e->plan.g.np, coords, sz)
-                               : local_size_c2c(e->plan.g.n, e->plan.g.np, coords, sz);
-  return align_up((size_t)std::max<long long>(L.alloc_max, 16), 256);
+  const long long b = Plan::buffer_bytes(e->plan.g.n, e->plan.g.np, coords, e->plan.g.r2c, e->plan.prec, e->plan.nprocs);
+  return align_up((size_t)b, 256);
 }
 
 struct IpcBlob {
@@ -556,7 +554,8 @@ int accfftb_plan_destroy(accfftb_plan* plan) {
   if (!(plan)) return fail(ACCFFTB_ERR_ARG, "null plan");                                          \
   if ((plan)->e.plan.g.r2c != (want_r2c))                                                           \
     return fail(ACCFFTB_ERR_ARG, (want_r2c) ? "this call needs an r2c plan" : "this call needs a c2c plan"); \
-  if (xyz != 7) return fail(ACCFFTB_ERR_UNSUPPORTED, "partial-axis transforms (xyz != 111) are not implemented");
+  if (xyz != 7) return fail(ACCFFTB_ERR_UNSUPPORTED, "partial-axis transforms (xyz != 111) are not implemented"); \
+  if (!(plan)->e.wired) return fail(ACCFFTB_ERR_STATE, "multi-rank plan used before its peers were attached");
 
 int accfftb_execute_r2c(accfftb_plan* plan, const void* data, void* data_out, double* timer, int xyz) {
   CHECK_PLAN(plan, true);
@@ -596,8 +595,10 @@ int accfftb_laplace(accfftb_plan* plan, const void* A, void* LA, double* timer) 
   CHECK_PLAN(plan, true);
   if (!A || !LA) return fail(ACCFFTB_ERR_ARG, "null data pointer");
   Engine* e = &plan->e;
+  int rc = ensure_spec(e);
+  if (rc) return rc;
   TimerScope ts(e, timer, 7);
-  return engine_finish(e, e->plan.execute_spectral(A, LA, OP_LAPLACE));
+  return engine_finish(e, e->plan.execute_spectral(A, LA, OP_LAPLACE, e->spec));
 }
 
 int accfftb_biharmonic(accfftb_plan* plan, const void* A, void* BA, double* timer) {
@@ -605,8 +606,10 @@ int accfftb_biharmonic(accfftb_plan* plan, const void* A, void* BA, double* time
   CHECK_PLAN(plan, true);
   if (!A || !BA) return fail(ACCFFTB_ERR_ARG, "null data pointer");
   Engine* e = &plan->e;
+  int rc = ensure_spec(e);
+  if (rc) return rc;
   TimerScope ts(e, timer, 7);
-  return engine_finish(e, e->plan.execute_spectral(A, BA, OP_BIHARMONIC));
+  return engine_finish(e, e->plan.execute_spectral(A, BA, OP_BIHARMONIC, e->spec));
 }
 
 int accfftb_grad(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int comps, double* timer) {

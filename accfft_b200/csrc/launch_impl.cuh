@@ -56,7 +56,7 @@ static int launch_one(const Launch& l, cudaStream_t st) {
   using C = Cfg<T, S>;
   const StageDesc& d = l.desc;
 #if ACCFFT_KIND == 0
-  const long long nb = (long long)d.nA * ((d.nB + C::TC - 1) / C::TC);
+  const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
   return launch_kernel(k_strided_c2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st);
 #elif ACCFFT_KIND == 1
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;

@@ -70,9 +70,10 @@ Launch Plan::fwd_z(const void* in, bool in_padded) const {
   for (int p = 0; p < P1; ++p) {
     const Blk kp = block_of(g.n2c, P1, p);
     const int r = rank_of(g.np, g.coords[0], p);
-    d.seg[p].base = offs(peerA[r], (long long)g.i1.start * kp.size, cs);
-    d.seg[p].strideA = (long long)g.n[1] * kp.size;
-    d.seg[p].strideB = kp.size;
+    const long long pp = pitch(kp.size);
+    d.seg[p].base = offs(peerA[r], (long long)g.i1.start * pp, cs);
+    d.seg[p].strideA = (long long)g.n[1] * pp;
+    d.seg[p].strideB = pp;
     d.seg[p].strideI = 1;
   }
   l.prec = prec;
@@ -89,21 +90,22 @@ Launch Plan::fwd_y() const {
   StageDesc d = blank();
   const int P0 = g.np[0];
   const int self = rank_of(g.np, g.coords[0], g.coords[1]);
+  const long long pk = pitch(g.k2.size);
   d.in = peerA[self];
   d.nA = g.i0.size;
   d.nB = g.k2.size;
-  d.inStrideA = (long long)g.n[1] * g.k2.size;
+  d.inStrideA = (long long)g.n[1] * pk;
   d.inStrideB = 1;
-  d.inStrideI = g.k2.size;
+  d.inStrideI = pk;
   d.tw = be->twiddle(prec, g.n[1]);
   set_segs_common(d, P0, ceil_blk(g.n[1], P0));
   for (int q = 0; q < P0; ++q) {
     const Blk k1q = block_of(g.n[1], P0, q);
     const int r = rank_of(g.np, q, g.coords[1]);
-    d.seg[q].base = offs(peerB[r], (long long)g.i0.start * k1q.size * g.k2.size, cs);
-    d.seg[q].strideA = (long long)k1q.size * g.k2.size;
+    d.seg[q].base = offs(peerB[r], (long long)g.i0.start * k1q.size * pk, cs);
+    d.seg[q].strideA = (long long)k1q.size * pk;
     d.seg[q].strideB = 1;
-    d.seg[q].strideI = g.k2.size;
+    d.seg[q].strideI = pk;
   }
   l.kind = K_STRIDED_C2C;
   l.prec = prec;
@@ -120,29 +122,45 @@ Launch Plan::fwd_x(void* out) const {
   StageDesc d = blank();
   const int self = rank_of(g.np, g.coords[0], g.coords[1]);
   const long long plane = (long long)g.k1.size * g.k2.size;
+  const long long pk = pitch(g.k2.size);
   d.in = peerB[self];
-  d.nA = 1;
-  d.nB = (int)plane;
-  d.inStrideA = 0;
-  d.inStrideB = 1;
-  d.inStrideI = plane;
   d.tw = be->twiddle(prec, g.n[0]);
   set_segs_common(d, 1, g.n[0]);
   d.seg[0].base = out;
-  d.seg[0].strideA = 0;
-  d.seg[0].strideB = 1;
-  d.seg[0].strideI = plane;
-  // global frequency indices of an output element (k0 = transform index, k1/k2 from the flat column index)
   d.n[0] = g.n[0];
   d.n[1] = g.n[1];
   d.n[2] = g.n[2];
   d.kind[0] = 0;
   d.off[0] = 0;
-  d.kind[1] = 3;
   d.off[1] = g.k1.start;
-  d.kind[2] = 4;
   d.off[2] = g.k2.start;
-  d.div = g.k2.size > 0 ? g.k2.size : 1;
+  if (pk == g.k2.size) {
+    // dense B: the (k1, k2) plane is one flat, line-aligned column index
+    d.nA = 1;
+    d.nB = (int)plane;
+    d.inStrideA = 0;
+    d.inStrideB = 1;
+    d.inStrideI = plane;
+    d.seg[0].strideA = 0;
+    d.seg[0].strideB = 1;
+    d.seg[0].strideI = plane;
+    // global frequency indices of an output element (k0 = transform index, k1/k2 from the flat column index)
+    d.kind[1] = 3;
+    d.kind[2] = 4;
+    d.div = g.k2.size > 0 ? g.k2.size : 1;
+  } else {
+    // pitched B -> dense user layout: columns are (a = k1, b = k2)
+    d.nA = g.k1.size;
+    d.nB = g.k2.size;
+    d.inStrideA = pk;
+    d.inStrideB = 1;
+    d.inStrideI = (long long)g.k1.size * pk;
+    d.seg[0].strideA = g.k2.size;
+    d.seg[0].strideB = 1;
+    d.seg[0].strideI = plane;
+    d.kind[1] = 1;
+    d.kind[2] = 2;
+  }
   l.kind = K_STRIDED_C2C;
   l.prec = prec;
   l.fftN = g.n[0];
@@ -159,20 +177,41 @@ Launch Plan::inv_x(const void* in) const {
   StageDesc d = blank();
   const int P0 = g.np[0];
   const long long plane = (long long)g.k1.size * g.k2.size;
+  const long long pk = pitch(g.k2.size);
   d.in = in;
-  d.nA = 1;
-  d.nB = (int)plane;
-  d.inStrideA = 0;
-  d.inStrideB = 1;
-  d.inStrideI = plane;
   d.tw = be->twiddle(prec, g.n[0]);
   set_segs_common(d, P0, ceil_blk(g.n[0], P0));
+  d.n[0] = g.n[0];
+  d.n[1] = g.n[1];
+  d.n[2] = g.n[2];
+  d.kind[0] = 0;
+  d.off[0] = 0;
+  d.off[1] = g.k1.start;
+  d.off[2] = g.k2.start;
+  if (pk == g.k2.size) {
+    d.nA = 1;
+    d.nB = (int)plane;
+    d.inStrideA = 0;
+    d.inStrideB = 1;
+    d.inStrideI = plane;
+    d.kind[1] = 3;
+    d.kind[2] = 4;
+    d.div = g.k2.size > 0 ? g.k2.size : 1;
+  } else {
+    d.nA = g.k1.size;
+    d.nB = g.k2.size;
+    d.inStrideA = g.k2.size;
+    d.inStrideB = 1;
+    d.inStrideI = plane;
+    d.kind[1] = 1;
+    d.kind[2] = 2;
+  }
   for (int q = 0; q < P0; ++q) {
     const int r = rank_of(g.np, q, g.coords[1]);
-    d.seg[q].base = offs(peerA[r], (long long)g.k1.start * g.k2.size, cs);
-    d.seg[q].strideA = 0;
+    d.seg[q].base = offs(peerA[r], (long long)g.k1.start * pk, cs);
+    d.seg[q].strideA = pk == g.k2.size ? 0 : pk;
     d.seg[q].strideB = 1;
-    d.seg[q].strideI = (long long)g.n[1] * g.k2.size;
+    d.seg[q].strideI = (long long)g.n[1] * pk;
   }
   l.kind = K_STRIDED_C2C;
   l.prec = prec;
@@ -190,21 +229,23 @@ Launch Plan::inv_y() const {
   StageDesc d = blank();
   const int P1 = g.np[1];
   const int self = rank_of(g.np, g.coords[0], g.coords[1]);
+  const long long pk = pitch(g.k2.size), pz = pitch(g.n2c);
   d.in = peerA[self];
   d.nA = g.i0.size;
   d.nB = g.k2.size;
-  d.inStrideA = (long long)g.n[1] * g.k2.size;
+  d.inStrideA = (long long)g.n[1] * pk;
   d.inStrideB = 1;
-  d.inStrideI = g.k2.size;
+  d.inStrideI = pk;
+  d.colShift = g.k2.size > 0 ? g.k2.start % pad_elems() : 0;   // destination rows are entered at column k2.start
   d.tw = be->twiddle(prec, g.n[1]);
   set_segs_common(d, P1, ceil_blk(g.n[1], P1));
   for (int p = 0; p < P1; ++p) {
     const Blk i1p = block_of(g.n[1], P1, p);
     const int r = rank_of(g.np, g.coords[0], p);
     d.seg[p].base = offs(peerB[r], g.k2.start, cs);
-    d.seg[p].strideA = (long long)i1p.size * g.n2c;
+    d.seg[p].strideA = (long long)i1p.size * pz;
     d.seg[p].strideB = 1;
-    d.seg[p].strideI = g.n2c;
+    d.seg[p].strideI = pz;
   }
   l.kind = K_STRIDED_C2C;
   l.prec = prec;
@@ -220,11 +261,12 @@ Launch Plan::inv_z(void* out, bool out_padded) const {
   Launch l{};
   StageDesc d = blank();
   const int self = rank_of(g.np, g.coords[0], g.coords[1]);
+  const long long pz = pitch(g.n2c);
   d.in = peerB[self];
   d.nA = g.i0.size;
   d.nB = g.i1.size;
-  d.inStrideA = (long long)g.n2c * g.i1.size;
-  d.inStrideB = g.n2c;
+  d.inStrideA = pz * g.i1.size;
+  d.inStrideB = pz;
   d.inStrideI = 1;
   d.tw = be->twiddle(prec, g.n[2]);
   set_segs_common(d, 1, g.n[2] + 2);
@@ -280,6 +322,21 @@ bool Plan::check_supported() {
   return true;
 }
 
+long long Plan::buffer_bytes(const int n[3], const int np[2], const int coords[2], bool r2c, Prec prec, int nprocs) {
+  Plan tmp;
+  tmp.prec = prec;
+  tmp.nprocs = nprocs;
+  const long long cs = prec == PREC_DOUBLE ? 16 : 8;
+  const int n2c = r2c ? n[2] / 2 + 1 : n[2];
+  const Blk i0 = block_of(n[0], np[0], coords[0]), i1 = block_of(n[1], np[1], coords[1]);
+  const Blk k2 = block_of(n2c, np[1], coords[1]), k1 = block_of(n[1], np[0], coords[0]);
+  const long long a = (long long)i0.size * n[1] * tmp.pitch(k2.size);
+  const long long b1 = (long long)n[0] * k1.size * tmp.pitch(k2.size);
+  const long long b2 = (long long)i0.size * i1.size * tmp.pitch(n2c);
+  const long long m = std::max(a, std::max(b1, b2));
+  return std::max<long long>(m * cs, 16);
+}
+
 static bool empty(const Launch& l) { return l.desc.nA <= 0 || l.desc.nB <= 0; }
 
 int Plan::execute_forward(const void* in, void* out, bool in_padded) {
@@ -308,21 +365,21 @@ int Plan::execute_inverse(const void* in, void* out, bool out_padded) {
   return 0;
 }
 
-int Plan::execute_spectral(const void* in, void* out, int op) {
+int Plan::execute_spectral(const void* in, void* out, int op, void* spec) {
   int rc;
-  const int self = rank_of(g.np, g.coords[0], g.coords[1]);
   Launch z = fwd_z(in, false);
   if (!empty(z) && (rc = be->launch(z))) return rc;
   if (nprocs > 1 && (rc = be->barrier())) return rc;
   Launch y = fwd_y();
   if (!empty(y) && (rc = be->launch(y))) return rc;
   if (nprocs > 1 && (rc = be->barrier())) return rc;
-  // X forward with the symbol multiply and the 1/N normalisation fused into its stores, in place in B
-  Launch x = fwd_x(peerB[self]);
+  // X forward with the symbol multiply and the 1/N normalisation fused into its stores, into `spec`
+  // (user spectrum layout), which the inverse X stage reads back
+  Launch x = fwd_x(spec);
   x.desc.op = op;
   x.desc.scale = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
   if (!empty(x) && (rc = be->launch(x))) return rc;
-  Launch xi = inv_x(peerB[self]);
+  Launch xi = inv_x(spec);
   if (!empty(xi) && (rc = be->launch(xi))) return rc;
   if (nprocs > 1 && (rc = be->barrier())) return rc;
   Launch yi = inv_y();

@@ -58,6 +58,16 @@ struct Plan {
   // exchange buffers of every rank of the comm as seen from this rank (self = local pointers)
   std::vector<void*> peerA, peerB;
   std::string error;
+  // Internal exchange buffers use a padded row pitch when there are peers: rows of A / B hold k2.size (or N2c)
+  // complex elements but start every `pad_elems()` elements (128 bytes), so that the 128-byte row segments the
+  // stage kernels store over NVLink are line aligned.  Single-rank plans keep dense rows.
+  int pad_elems() const { return nprocs > 1 ? (prec == PREC_DOUBLE ? 8 : 16) : 1; }
+  long long pitch(long long n) const {
+    const long long p = pad_elems();
+    return (n + p - 1) / p * p;
+  }
+  // bytes needed for each of the two exchange buffers of the rank at `coords`
+  static long long buffer_bytes(const int n[3], const int np[2], const int coords[2], bool r2c, Prec prec, int nprocs);
 
   // the three forward and three inverse stages; `in` / `out` are the user's buffers
   Launch fwd_z(const void* in, bool in_padded) const;
@@ -71,7 +81,7 @@ struct Plan {
   int execute_forward(const void* in, void* out, bool in_padded);
   int execute_inverse(const void* in, void* out, bool out_padded);
   // fused forward -> spectral symbol -> inverse (laplace / biharmonic; src/operators_gpu.txx:280-334, :555-609)
-  int execute_spectral(const void* in, void* out, int op);
+  int execute_spectral(const void* in, void* out, int op, void* spec);
   // grad (src/operators_gpu.txx:72-278): one forward into `spec` (normalised), then per selected component
   // an inverse whose X stage multiplies by i*k_axis on load.  comps: bit 0 = x, bit 1 = y, bit 2 = z.
   int execute_grad(const void* in, void* const outs[3], int comps, void* spec);

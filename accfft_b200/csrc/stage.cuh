@@ -52,6 +52,8 @@ struct StageDesc {
   double scale;
   int opOnLoad;          // 1: apply `op` to the INPUT elements (inverse X stage of grad) instead of the outputs
   int accumulate;        // 1: outputs are added to the destination (divergence sums three spectra)
+  int colShift;          // strided kernels: tiles start at column -colShift so that tile origins are line aligned
+                         // in a destination whose rows this rank enters at an unaligned offset (inverse Y stage)
   int inv;               // 1: inverse transform (sign +1), done as swap(re,im) . forward . swap(re,im)
 };
 
@@ -93,8 +95,12 @@ ACC_HD cplx<T> apply_op(const StageDesc& d, cplx<T> v, int k, int a, int b) {
   if (d.op == OP_NONE) return v;
   if (d.op == OP_SCALE) return {T(v.x * d.scale), T(v.y * d.scale)};
   if (d.op == OP_GRAD) {
+    // The reference differentiates with a REAL transform along the axis (src/operators_gpu.txx:172-278), i.e. it
+    // only ever sees X <= N/2 and c2r implies the mirrored half: the mode pair +-floor(N/2) is zeroed as a pair.
+    // On a full (c2c) axis that means X == N/2 and X == N - N/2 (the same index when N is even).
     const int ax = d.opAxis;
-    const double w = d.scale * (double)wave_number(freq_index(d, ax, k, a, b), d.n[ax]);
+    const int X = freq_index(d, ax, k, a, b), N = d.n[ax];
+    const double w = (X == N - N / 2) ? 0.0 : d.scale * (double)wave_number(X, N);
     return {T(-w * v.y), T(w * v.x)};
   }
   const long long wx = wave_number(freq_index(d, 0, k, a, b), d.n[0]);
@@ -133,11 +139,11 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
   constexpr int RL = S::radix(S::NP - 1), NBL = S::nb(S::NP - 1), CNTL = S::cnt(S::NP - 1);
   const int tid = ctx.tid();
   const int c = tid % TC, t = tid / TC;
-  const int tpa = (d.nB + TC - 1) / TC;
+  const int tpa = (d.nB + d.colShift + TC - 1) / TC;
   const long long tile = ctx.bid();
   const int a = (int)(tile / tpa);
-  const int b = (int)(tile % tpa) * TC + c;
-  const bool valid = b < d.nB;
+  const int b = (int)(tile % tpa) * TC + c - d.colShift;
+  const bool valid = b >= 0 && b < d.nB;
   const bool inv = d.inv != 0;
   const bool simple = stage_is_simple(d);
   cplx<T> w1[S::NTW];

@@ -308,6 +308,9 @@ def grad(x: np.ndarray, axis: int) -> np.ndarray:
     The fast path transforms along one axis only; mathematically identical."""
     n = x.shape
     k = wave_numbers(n[axis])
+    # the reference transforms along the axis with r2c/c2r, so it only sees X <= N/2; c2r implies the mirrored
+    # half, hence the pair +-floor(N/2) is zeroed as a pair (matters only for odd N)
+    k[n[axis] - n[axis] // 2 if n[axis] > 1 else 0] = 0.0
     shape = [1, 1, 1]
     shape[axis] = n[axis]
     X = np.fft.fft(np.asarray(x, np.float64), axis=axis)

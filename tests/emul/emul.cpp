@@ -112,7 +112,7 @@ static void emu_launch_sched(const Launch& l) {
   const StageDesc& d = l.desc;
   switch (l.kind) {
     case K_STRIDED_C2C: {
-      const long long nb = (long long)d.nA * ((d.nB + C::TC - 1) / C::TC);
+      const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
       run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) { strided_c2c_body<T, S, C::TC>(d, c); });
       break;
     }
@@ -197,7 +197,7 @@ struct EmuWorld {
   Prec prec;
   std::vector<EmuBackend> be;
   std::vector<Plan> plans;
-  std::vector<std::vector<char>> bufA, bufB;
+  std::vector<std::vector<char>> bufA, bufB, spec;
   pthread_barrier_t bar;
 };
 int EmuBackend::barrier() {
@@ -219,6 +219,7 @@ void* emu_world_create(const int* n, int P0, int P1, int r2c, int prec) {
   w->plans.resize(w->nprocs);
   w->bufA.resize(w->nprocs);
   w->bufB.resize(w->nprocs);
+  w->spec.resize(w->nprocs);
   pthread_barrier_init(&w->bar, nullptr, w->nprocs);
   const int sz = prec == PREC_DOUBLE ? 8 : 4;
   for (int r = 0; r < w->nprocs; ++r) {
@@ -231,8 +232,10 @@ void* emu_world_create(const int* n, int P0, int P1, int r2c, int prec) {
     p.be = &w->be[r];
     p.nprocs = w->nprocs;
     // +64 bytes so that out-of-range writes are more likely to be caught by the canary check below
-    w->bufA[r].assign((size_t)p.g.L.alloc_max + 64, (char)0xEE);
-    w->bufB[r].assign((size_t)p.g.L.alloc_max + 64, (char)0xEE);
+    const size_t bb = (size_t)Plan::buffer_bytes(w->n, w->np, coords, w->r2c, w->prec, w->nprocs);
+    w->bufA[r].assign(bb + 64, (char)0xEE);
+    w->bufB[r].assign(bb + 64, (char)0xEE);
+    w->spec[r].assign(bb + 64, (char)0xEE);
   }
   for (int r = 0; r < w->nprocs; ++r) {
     Plan& p = w->plans[r];
@@ -276,10 +279,41 @@ int emu_execute(void* h, int mode, void** in, void** out, int padded) {
       Plan& p = w->plans[r];
       if (mode == 0) rc[r] = p.execute_forward(in[r], out[r], padded != 0);
       else if (mode == 1) rc[r] = p.execute_inverse(in[r], out[r], padded != 0);
-      else if (mode == 2) rc[r] = p.execute_spectral(in[r], out[r], OP_LAPLACE);
-      else rc[r] = p.execute_spectral(in[r], out[r], OP_BIHARMONIC);
+      else if (mode == 2) rc[r] = p.execute_spectral(in[r], out[r], OP_LAPLACE, w->spec[r].data());
+      else rc[r] = p.execute_spectral(in[r], out[r], OP_BIHARMONIC, w->spec[r].data());
     });
   }
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w->nprocs; ++r)
+    if (rc[r]) return rc[r];
+  return canaries_ok(w) ? 0 : -99;
+}
+
+// grad: outs = 3 arrays of per-rank pointers (x, y, z components); divergence: ins likewise
+int emu_execute_grad(void* h, void** in, void** ox, void** oy, void** oz, int comps) {
+  EmuWorld* w = (EmuWorld*)h;
+  std::vector<std::thread> th;
+  std::vector<int> rc(w->nprocs, 0);
+  for (int r = 0; r < w->nprocs; ++r)
+    th.emplace_back([&, r]() {
+      void* outs[3] = {ox[r], oy[r], oz[r]};
+      rc[r] = w->plans[r].execute_grad(in[r], outs, comps, w->spec[r].data());
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w->nprocs; ++r)
+    if (rc[r]) return rc[r];
+  return canaries_ok(w) ? 0 : -99;
+}
+
+int emu_execute_div(void* h, void** ix, void** iy, void** iz, void** out) {
+  EmuWorld* w = (EmuWorld*)h;
+  std::vector<std::thread> th;
+  std::vector<int> rc(w->nprocs, 0);
+  for (int r = 0; r < w->nprocs; ++r)
+    th.emplace_back([&, r]() {
+      const void* ins[3] = {ix[r], iy[r], iz[r]};
+      rc[r] = w->plans[r].execute_divergence(ins, out[r], w->spec[r].data());
+    });
   for (auto& t : th) t.join();
   for (int r = 0; r < w->nprocs; ++r)
     if (rc[r]) return rc[r];

@@ -48,6 +48,11 @@ def lib():
         _lib.emu_execute.restype = ctypes.c_int
         _lib.emu_execute.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
                                      ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
+        pp = ctypes.POINTER(ctypes.c_void_p)
+        _lib.emu_execute_grad.restype = ctypes.c_int
+        _lib.emu_execute_grad.argtypes = [ctypes.c_void_p, pp, pp, pp, pp, ctypes.c_int]
+        _lib.emu_execute_div.restype = ctypes.c_int
+        _lib.emu_execute_div.argtypes = [ctypes.c_void_p, pp, pp, pp, pp]
     return _lib
 
 
@@ -147,6 +152,44 @@ class World:
             s1 = orc.block(n[1], self.np_[1], c[1])[0]
             blocks.append(outs[r][:s0 * s1 * n[2]].reshape(s0, s1, n[2]).copy())
         return blocks
+
+
+def _local_real(w, x_global):
+    return [np.ascontiguousarray(orc.local_input(x_global, w.n, w.np_, w.coords(r)).astype(w.rdt))
+            for r in range(w.nprocs)]
+
+
+def _ptrs(arrs):
+    return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def _blocks_real(w, outs):
+    n = w.n
+    blocks = []
+    for r in range(w.nprocs):
+        c = w.coords(r)
+        s0 = orc.block(n[0], w.np_[0], c[0])[0]
+        s1 = orc.block(n[1], w.np_[1], c[1])[0]
+        blocks.append(outs[r][:s0 * s1 * n[2]].reshape(s0, s1, n[2]).copy())
+    return blocks
+
+
+def grad(w, x_global, comps=7):
+    ins = _local_real(w, x_global)
+    outs = [w.alloc_out() for _ in range(3)]
+    rc = lib().emu_execute_grad(w.h, _ptrs(ins), _ptrs(outs[0]), _ptrs(outs[1]), _ptrs(outs[2]), comps)
+    if rc:
+        raise RuntimeError(f"emu_execute_grad rc={rc}")
+    return [_blocks_real(w, o) for o in outs]
+
+
+def divergence(w, ax, ay, az):
+    ins = [_local_real(w, v) for v in (ax, ay, az)]
+    out = w.alloc_out()
+    rc = lib().emu_execute_div(w.h, _ptrs(ins[0]), _ptrs(ins[1]), _ptrs(ins[2]), _ptrs(out))
+    if rc:
+        raise RuntimeError(f"emu_execute_div rc={rc}")
+    return _blocks_real(w, out)
 
 
 if __name__ == "__main__":
