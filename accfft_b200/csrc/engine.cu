@@ -144,8 +144,9 @@ struct Engine {
 struct ScopedProfile {
   Engine* e;
   Engine::Rec r;
-  ScopedProfile(Engine* e_, int slot) : e(e_) {
-    if (e->profiling) {
+  bool on;
+  ScopedProfile(Engine* e_, int slot) : e(e_), on(e_->profiling && slot >= 0) {
+    if (on) {
       r.slot = slot;
       r.a = e->take_event();
       r.b = e->take_event();
@@ -153,7 +154,7 @@ struct ScopedProfile {
     }
   }
   ~ScopedProfile() {
-    if (e->profiling) {
+    if (on) {
       cudaEventRecord(r.b, e->stream);
       e->recs.push_back(r);
     }
@@ -189,10 +190,10 @@ struct ScopedTimer {
   Engine* e;
   double* acc;
   ScopedTimer(Engine* e_, double* acc_) : e(e_), acc(acc_) {
-    if (e->timing) cudaEventRecord(e->ev[0], e->stream);
+    if (e->timing && acc) cudaEventRecord(e->ev[0], e->stream);
   }
   ~ScopedTimer() {
-    if (e->timing) {
+    if (e->timing && acc) {
       cudaEventRecord(e->ev[1], e->stream);
       cudaEventSynchronize(e->ev[1]);
       float ms = 0;
@@ -204,8 +205,8 @@ struct ScopedTimer {
 
 int CudaBackend::launch(const Launch& l) {
   if (!l.desc.tw) return fail(ACCFFTB_ERR_STATE, "twiddle table allocation failed");
-  ScopedTimer tm(e, &e->t_fft);
-  ScopedProfile pf(e, l.slot);
+  ScopedTimer tm(e, l.dry ? nullptr : &e->t_fft);
+  ScopedProfile pf(e, l.dry ? -1 : l.slot);
   int rc = -1;
   const int sel = (int)l.kind * 2 + (int)l.prec;
   switch (sel) {
@@ -221,7 +222,7 @@ int CudaBackend::launch(const Launch& l) {
   }
   if (rc == -1) return fail(ACCFFTB_ERR_UNSUPPORTED, "no kernel schedule for length " + std::to_string(l.fftN));
   if (rc != 0) return cuda_fail((cudaError_t)rc, "stage kernel launch");
-  e->launches++;
+  if (!l.dry) e->launches++;
   return 0;
 }
 
@@ -429,6 +430,9 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
     err = cudaMalloc((void**)&e->slab, e->slab_bytes);
   }
   if (err == cudaSuccess) err = cudaMemset(e->slab + 2 * e->bufsz, 0, kFlagBytes);
+  // spectrum scratch of the operators: allocated now, never inside a collective call (cudaMalloc synchronises
+  // the device, which must not happen while a peer's barrier kernel waits for this rank)
+  if (err == cudaSuccess && kind == ACCFFTB_R2C) err = cudaMalloc(&e->spec, e->bufsz);
   if (err == cudaSuccess) err = cudaMalloc((void**)&e->status_d, sizeof(int));
   if (err == cudaSuccess) err = cudaMemset(e->status_d, 0, sizeof(int));
   if (err == cudaSuccess) err = cudaEventCreate(&e->ev[0]);
@@ -442,6 +446,18 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
   }
   wire_self(e);
   e->wired = pl.nprocs == 1;
+  {
+    // load every kernel now (see Plan::prepare)
+    cudaFuncAttributes fa;
+    err = cudaFuncGetAttributes(&fa, k_barrier);
+    int rc = err == cudaSuccess ? pl.prepare() : (int)err;
+    if (rc) {
+      if (err != cudaSuccess) cuda_fail(err, "accfftb_plan_create (kernel load)");
+      engine_free(e);
+      delete p;
+      return nullptr;
+    }
+  }
   return p;
 }
 
@@ -586,8 +602,7 @@ int accfftb_execute_c2c(accfftb_plan* plan, int direction, const void* data, voi
 
 static int ensure_spec(Engine* e) {
   if (e->spec) return 0;
-  CU(cudaMalloc(&e->spec, e->bufsz));
-  return 0;
+  return fail(ACCFFTB_ERR_STATE, "operator scratch buffer missing");
 }
 
 int accfftb_laplace(accfftb_plan* plan, const void* A, void* LA, double* timer) {

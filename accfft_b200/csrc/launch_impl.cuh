@@ -40,7 +40,15 @@ __global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_c2r(const 
 }
 
 template <class K>
-static int launch_kernel(K kernel, long long nblocks, int threads, int smem, const StageDesc& d, cudaStream_t st) {
+static int launch_kernel(K kernel, long long nblocks, int threads, int smem, const StageDesc& d, cudaStream_t st,
+                         bool dry) {
+  if (dry) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);   // forces the (lazy) load of the kernel
+    if (e == cudaSuccess && smem > 48 * 1024)
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return (int)e;
+  }
   if (nblocks <= 0) return 0;
   if (nblocks > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
   if (smem > 48 * 1024) {
@@ -57,16 +65,16 @@ static int launch_one(const Launch& l, cudaStream_t st) {
   const StageDesc& d = l.desc;
 #if ACCFFT_KIND == 0
   const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
-  return launch_kernel(k_strided_c2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st);
+  return launch_kernel(k_strided_c2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
 #elif ACCFFT_KIND == 1
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-  return launch_kernel(k_contig_c2c<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st);
+  return launch_kernel(k_contig_c2c<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
 #elif ACCFFT_KIND == 2
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-  return launch_kernel(k_contig_r2c<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st);
+  return launch_kernel(k_contig_r2c<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
 #else
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-  return launch_kernel(k_contig_c2r<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st);
+  return launch_kernel(k_contig_c2r<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
 #endif
 }
 

@@ -70,7 +70,7 @@ Launch Plan::fwd_z(const void* in, bool in_padded) const {
   for (int p = 0; p < P1; ++p) {
     const Blk kp = block_of(g.n2c, P1, p);
     const int r = rank_of(g.np, g.coords[0], p);
-    const long long pp = pitch(kp.size);
+    const long long pp = kp.size;   // A is dense
     d.seg[p].base = offs(peerA[r], (long long)g.i1.start * pp, cs);
     d.seg[p].strideA = (long long)g.n[1] * pp;
     d.seg[p].strideB = pp;
@@ -94,9 +94,9 @@ Launch Plan::fwd_y() const {
   d.in = peerA[self];
   d.nA = g.i0.size;
   d.nB = g.k2.size;
-  d.inStrideA = (long long)g.n[1] * pk;
+  d.inStrideA = (long long)g.n[1] * g.k2.size;
   d.inStrideB = 1;
-  d.inStrideI = pk;
+  d.inStrideI = g.k2.size;
   d.tw = be->twiddle(prec, g.n[1]);
   set_segs_common(d, P0, ceil_blk(g.n[1], P0));
   for (int q = 0; q < P0; ++q) {
@@ -177,7 +177,6 @@ Launch Plan::inv_x(const void* in) const {
   StageDesc d = blank();
   const int P0 = g.np[0];
   const long long plane = (long long)g.k1.size * g.k2.size;
-  const long long pk = pitch(g.k2.size);
   d.in = in;
   d.tw = be->twiddle(prec, g.n[0]);
   set_segs_common(d, P0, ceil_blk(g.n[0], P0));
@@ -188,30 +187,21 @@ Launch Plan::inv_x(const void* in) const {
   d.off[0] = 0;
   d.off[1] = g.k1.start;
   d.off[2] = g.k2.start;
-  if (pk == g.k2.size) {
-    d.nA = 1;
-    d.nB = (int)plane;
-    d.inStrideA = 0;
-    d.inStrideB = 1;
-    d.inStrideI = plane;
-    d.kind[1] = 3;
-    d.kind[2] = 4;
-    d.div = g.k2.size > 0 ? g.k2.size : 1;
-  } else {
-    d.nA = g.k1.size;
-    d.nB = g.k2.size;
-    d.inStrideA = g.k2.size;
-    d.inStrideB = 1;
-    d.inStrideI = plane;
-    d.kind[1] = 1;
-    d.kind[2] = 2;
-  }
+  // user spectrum and A are both dense: the (k1, k2) plane is one flat column index
+  d.nA = 1;
+  d.nB = (int)plane;
+  d.inStrideA = 0;
+  d.inStrideB = 1;
+  d.inStrideI = plane;
+  d.kind[1] = 3;
+  d.kind[2] = 4;
+  d.div = g.k2.size > 0 ? g.k2.size : 1;
   for (int q = 0; q < P0; ++q) {
     const int r = rank_of(g.np, q, g.coords[1]);
-    d.seg[q].base = offs(peerA[r], (long long)g.k1.start * pk, cs);
-    d.seg[q].strideA = pk == g.k2.size ? 0 : pk;
+    d.seg[q].base = offs(peerA[r], (long long)g.k1.start * g.k2.size, cs);
+    d.seg[q].strideA = 0;
     d.seg[q].strideB = 1;
-    d.seg[q].strideI = (long long)g.n[1] * pk;
+    d.seg[q].strideI = (long long)g.n[1] * g.k2.size;
   }
   l.kind = K_STRIDED_C2C;
   l.prec = prec;
@@ -229,13 +219,13 @@ Launch Plan::inv_y() const {
   StageDesc d = blank();
   const int P1 = g.np[1];
   const int self = rank_of(g.np, g.coords[0], g.coords[1]);
-  const long long pk = pitch(g.k2.size), pz = pitch(g.n2c);
+  const long long pz = pitch(g.n2c);
   d.in = peerA[self];
   d.nA = g.i0.size;
   d.nB = g.k2.size;
-  d.inStrideA = (long long)g.n[1] * pk;
+  d.inStrideA = (long long)g.n[1] * g.k2.size;
   d.inStrideB = 1;
-  d.inStrideI = pk;
+  d.inStrideI = g.k2.size;
   d.colShift = g.k2.size > 0 ? g.k2.start % pad_elems() : 0;   // destination rows are entered at column k2.start
   d.tw = be->twiddle(prec, g.n[1]);
   set_segs_common(d, P1, ceil_blk(g.n[1], P1));
@@ -330,7 +320,7 @@ long long Plan::buffer_bytes(const int n[3], const int np[2], const int coords[2
   const int n2c = r2c ? n[2] / 2 + 1 : n[2];
   const Blk i0 = block_of(n[0], np[0], coords[0]), i1 = block_of(n[1], np[1], coords[1]);
   const Blk k2 = block_of(n2c, np[1], coords[1]), k1 = block_of(n[1], np[0], coords[0]);
-  const long long a = (long long)i0.size * n[1] * tmp.pitch(k2.size);
+  const long long a = (long long)i0.size * n[1] * k2.size;
   const long long b1 = (long long)n[0] * k1.size * tmp.pitch(k2.size);
   const long long b2 = (long long)i0.size * i1.size * tmp.pitch(n2c);
   const long long m = std::max(a, std::max(b1, b2));
@@ -338,6 +328,15 @@ long long Plan::buffer_bytes(const int n[3], const int np[2], const int coords[2
 }
 
 static bool empty(const Launch& l) { return l.desc.nA <= 0 || l.desc.nB <= 0; }
+
+int Plan::prepare() {
+  Launch ls[6] = {fwd_z(nullptr, false), fwd_y(), fwd_x(nullptr), inv_x(nullptr), inv_y(), inv_z(nullptr, false)};
+  for (Launch& l : ls) {
+    l.dry = true;
+    if (int rc = be->launch(l)) return rc;
+  }
+  return 0;
+}
 
 int Plan::execute_forward(const void* in, void* out, bool in_padded) {
   int rc;
@@ -406,13 +405,6 @@ int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spe
   for (int ax = 0; ax < 3; ++ax) {
     if (!(comps & (1 << ax))) continue;
     Launch xi = inv_x(spec);
-    // same (k0, k1, k2) bookkeeping as the forward X stage: the layouts are identical
-    for (int i = 0; i < 3; ++i) {
-      xi.desc.n[i] = x.desc.n[i];
-      xi.desc.kind[i] = x.desc.kind[i];
-      xi.desc.off[i] = x.desc.off[i];
-    }
-    xi.desc.div = x.desc.div;
     xi.desc.op = OP_GRAD;
     xi.desc.opAxis = ax;
     xi.desc.scale = 1.0;

@@ -20,6 +20,7 @@ struct Launch {
   Prec prec;
   int fftN;        // length of the complex engine transform (M = N/2 for r2c / c2r)
   bool inverse;
+  bool dry;        // true: only load / configure the kernel (plan time), do not launch
   int slot;        // profiling slot: 0 fwd Z, 1 fwd Y, 2 fwd X, 3 inv X, 4 inv Y, 5 inv Z  (6 = barrier)
   StageDesc desc;
 };
@@ -58,9 +59,11 @@ struct Plan {
   // exchange buffers of every rank of the comm as seen from this rank (self = local pointers)
   std::vector<void*> peerA, peerB;
   std::string error;
-  // Internal exchange buffers use a padded row pitch when there are peers: rows of A / B hold k2.size (or N2c)
+  // Buffer B uses a padded row pitch when there are peers: its rows hold k2.size (forward) or N2c (inverse)
   // complex elements but start every `pad_elems()` elements (128 bytes), so that the 128-byte row segments the
-  // stage kernels store over NVLink are line aligned.  Single-rank plans keep dense rows.
+  // Y stages store over NVLink are line aligned.  Buffer A stays dense: its NVLink writers are the Z stage (long
+  // contiguous runs) and the inverse X stage, whose flat (k1,k2) tiles are line aligned exactly when A is dense.
+  // Single-rank plans keep everything dense.
   int pad_elems() const { return nprocs > 1 ? (prec == PREC_DOUBLE ? 8 : 16) : 1; }
   long long pitch(long long n) const {
     const long long p = pad_elems();
@@ -78,6 +81,9 @@ struct Plan {
   Launch inv_z(void* out, bool out_padded) const;
 
   bool check_supported();
+  // Load and configure every kernel the plan can launch (CUDA loads kernels lazily, and a first-use load may
+  // synchronise the context -- which must not happen while another rank's barrier kernel is spinning).
+  int prepare();
   int execute_forward(const void* in, void* out, bool in_padded);
   int execute_inverse(const void* in, void* out, bool out_padded);
   // fused forward -> spectral symbol -> inverse (laplace / biharmonic; src/operators_gpu.txx:280-334, :555-609)

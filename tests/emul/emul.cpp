@@ -185,7 +185,7 @@ struct EmuBackend : Backend {
     return ref.data();
   }
   int launch(const Launch& l) override {
-    emu_launch(l);
+    if (!l.dry) emu_launch(l);
     return 0;
   }
   int barrier() override;
