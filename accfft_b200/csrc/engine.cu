@@ -28,6 +28,8 @@ int accfft_launch_k0_p1(const Launch&, cudaStream_t);
 int accfft_launch_k1_p1(const Launch&, cudaStream_t);
 int accfft_launch_k2_p1(const Launch&, cudaStream_t);
 int accfft_launch_k3_p1(const Launch&, cudaStream_t);
+int accfft_launch_k4_p0(const Launch&, cudaStream_t);   // TMA-pipelined strided stage; -2 = does not qualify
+int accfft_launch_k4_p1(const Launch&, cudaStream_t);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -66,24 +68,32 @@ struct BarrierDesc {
   int* status;   // device word, set to 1 on timeout
 };
 
-__global__ void k_barrier(const __grid_constant__ BarrierDesc b) {
-  const int q = (int)threadIdx.x;
-  if (q >= b.nprocs) return;
-  __threadfence_system();
-  unsigned long long* remote = b.flags[q] + b.rank;
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(b.epoch) : "memory");
-  const unsigned long long* mine = b.flags[b.rank] + q;
-  const long long t0 = clock64();
-  for (;;) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-    if (v >= b.epoch) break;
-    if (clock64() - t0 > b.timeout_cycles) {
-      *b.status = 1;
-      break;
-    }
-    __nanosleep(200);
+__global__ void __launch_bounds__(32) k_barrier(const __grid_constant__ BarrierDesc b) {
+  // one warp: lane q signals ranks q, q+32, ... and then waits for them.  The stage kernel that precedes this launch
+  // on the stream has completed, i.e. its (peer) stores are performed; the system-scope release orders them before
+  // the flag, the acquire orders the peers' stores before everything that follows on this stream.
+  for (int q = (int)threadIdx.x; q < b.nprocs; q += 32) {
+    unsigned long long* remote = b.flags[q] + b.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(b.epoch) : "memory");
   }
+  for (int q = (int)threadIdx.x; q < b.nprocs; q += 32) {
+    const unsigned long long* mine = b.flags[b.rank] + q;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= b.epoch) break;
+      if (++spins > 64) {   // peers normally arrive within a few microseconds: spin first, back off later
+        if (clock64() - t0 > b.timeout_cycles) {
+          *b.status = 1;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+  }
+  __syncwarp();
   __threadfence_system();
 }
 
@@ -210,8 +220,15 @@ int CudaBackend::launch(const Launch& l) {
   int rc = -1;
   const int sel = (int)l.kind * 2 + (int)l.prec;
   switch (sel) {
-    case 0: rc = accfft_launch_k0_p0(l, e->stream); break;
-    case 1: rc = accfft_launch_k0_p1(l, e->stream); break;
+    case 0:
+      // dry (plan-time) launches load BOTH variants; at run time the TMA kernel declines (-2) what it cannot take
+      rc = accfft_launch_k4_p0(l, e->stream);
+      if (rc == -2 || (l.dry && rc == 0)) rc = accfft_launch_k0_p0(l, e->stream);
+      break;
+    case 1:
+      rc = accfft_launch_k4_p1(l, e->stream);
+      if (rc == -2 || (l.dry && rc == 0)) rc = accfft_launch_k0_p1(l, e->stream);
+      break;
     case 2: rc = accfft_launch_k1_p0(l, e->stream); break;
     case 3: rc = accfft_launch_k1_p1(l, e->stream); break;
     case 4: rc = accfft_launch_k2_p0(l, e->stream); break;
@@ -238,7 +255,7 @@ int CudaBackend::barrier() {
   b.epoch = ++e->epoch;
   b.timeout_cycles = 20LL * 1000 * 1000 * 1000;   // ~10 s at 2 GHz: a peer died or diverged
   b.status = e->status_d;
-  k_barrier<<<1, 256, 0, e->stream>>>(b);
+  k_barrier<<<1, 32, 0, e->stream>>>(b);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cuda_fail(err, "barrier kernel launch");
   e->launches++;

@@ -35,6 +35,10 @@ struct Cfg {
   static constexpr int PC = (S::G >= ACCFFT_CONTIG_THREADS) ? 1 : ACCFFT_CONTIG_THREADS / S::G;
   static constexpr int CONTIG_THREADS = S::G * PC;
   static constexpr int CONTIG_SMEM = S::SMEM_ELEMS * PC * (int)sizeof(cplx<T>);
+  // staged stores (stage.cuh: staged_flush): room for the PC x NOUT outputs behind the transform scratch,
+  // NOUT = N (c2c) or N + 1 (r2c); N + 2 keeps the region a multiple of 16 bytes for both
+  // (the region starts at an even element index so that it is 16-byte aligned for float as well)
+  static constexpr int CONTIG_STAGED_SMEM = (((S::SMEM_ELEMS * PC + 1) & ~1) + (S::N + 2) * PC) * (int)sizeof(cplx<T>);
 };
 
 }  // namespace accfft_b200

@@ -3,8 +3,12 @@
 // (kind, precision) pair for every line of schedules.def so that the kernels compile in parallel.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "kernel_cfg.hpp"
 #include "plan.hpp"
+#if ACCFFT_KIND == 4
+#include "stage_tma.cuh"
+#endif
 
 namespace accfft_b200 {
 
@@ -16,6 +20,17 @@ struct CudaCtx {
     return accfft_smem_raw;
   }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
+  // bulk (TMA) copy shared -> global; the destination may be a peer-mapped buffer (NVLink).  16-byte aligned
+  // addresses and size.  Generic-proxy writes to the source must be fenced (bulk_fence) and CTA-synchronised first.
+  __device__ __forceinline__ void bulk_fence() const { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+  __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) const {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  // the CTA may exit / reuse the staging buffer once the copies have READ their source
+  __device__ __forceinline__ void bulk_wait() const { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 };
 
 template <class T, class S>
@@ -59,25 +74,131 @@ static int launch_kernel(K kernel, long long nblocks, int threads, int smem, con
   return (int)cudaGetLastError();
 }
 
+#if ACCFFT_KIND != 4
+// staged stores can be switched off for A/B measurements: ACCFFT_B200_STAGED=0
+static bool staged_enabled() {
+  static const int on = [] {
+    const char* e = getenv("ACCFFT_B200_STAGED");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return on != 0;
+}
+
 template <class T, class S>
 static int launch_one(const Launch& l, cudaStream_t st) {
   using C = Cfg<T, S>;
+#if ACCFFT_KIND == 1 || ACCFFT_KIND == 2
+  StageDesc d = l.desc;
+  d.staged = (d.nseg > 1 && d.op == OP_NONE && d.accumulate == 0 && staged_enabled()) ? 1 : 0;
+  const int contig_smem = l.dry || d.staged ? C::CONTIG_STAGED_SMEM : C::CONTIG_SMEM;
+#else
   const StageDesc& d = l.desc;
+#endif
 #if ACCFFT_KIND == 0
   const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
   return launch_kernel(k_strided_c2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
 #elif ACCFFT_KIND == 1
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-  return launch_kernel(k_contig_c2c<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
+  return launch_kernel(k_contig_c2c<T, S>, nb, C::CONTIG_THREADS, contig_smem, d, st, l.dry);
 #elif ACCFFT_KIND == 2
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-  return launch_kernel(k_contig_r2c<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
+  return launch_kernel(k_contig_r2c<T, S>, nb, C::CONTIG_THREADS, contig_smem, d, st, l.dry);
 #else
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
   return launch_kernel(k_contig_c2r<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
 #endif
 }
 
+#endif
+#if ACCFFT_KIND == 4
+// ---- TMA-pipelined strided stage (stage_tma.cuh) ------------------------------------------------------------
+// returns -2 when the launch does not qualify (caller falls back to k_strided_c2c)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+static bool tma_enabled() {
+  static const int on = [] {
+    const char* e = getenv("ACCFFT_B200_TMA");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return on != 0;
+}
+static int sm_count() {
+  static thread_local int dev_cached = -1, sms = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    dev_cached = dev;
+  }
+  return sms > 0 ? sms : 148;
+}
+
+template <class T, class S>
+static int launch_tma(const Launch& l, cudaStream_t st) {
+  using C0 = Cfg<T, S>;
+  using C = TmaCfg<T, S, C0::TC>;
+  if constexpr (!C::OK) {
+    return -2;
+  } else {
+    const StageDesc& d = l.desc;
+    auto kernel = k_strided_tma<T, S, C0::TC>;
+    if (l.dry) {
+      cudaFuncAttributes fa;
+      cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+      encode_tiled_fn();
+      sm_count();
+      return (int)e;
+    }
+    constexpr long long es = C::ES;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!tma_enabled() || !enc || d.inStrideB != 1 || ((uintptr_t)d.in & 15) || (d.inStrideI * es) % 16 != 0 ||
+        (d.nA > 1 && (d.inStrideA * es) % 16 != 0) || d.inStrideI * es >= (1LL << 40) || d.inStrideA * es >= (1LL << 40))
+      return -2;
+    const int tpa = (d.nB + d.colShift + C0::TC - 1) / C0::TC;
+    const long long ntiles = (long long)d.nA * tpa;
+    if (ntiles <= 0) return 0;
+    alignas(64) CUtensorMap map;
+    constexpr unsigned E = (unsigned)(es / 8);
+    const cuuint64_t gdim[3] = {(cuuint64_t)d.nB * E, (cuuint64_t)S::N, (cuuint64_t)d.nA};
+    const cuuint64_t gstr[2] = {(cuuint64_t)(d.inStrideI * es),
+                                (cuuint64_t)((d.nA > 1 ? d.inStrideA : d.inStrideI * S::N) * es)};
+    const cuuint32_t box[3] = {(cuuint32_t)(C0::TC * E), (cuuint32_t)C::BOXR, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(d.in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return -2;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    long long grid = (long long)sm_count() * C::CTAS;
+    if (grid > ntiles) grid = ntiles;
+    kernel<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(d, map, ntiles);
+    return (int)cudaGetLastError();
+  }
+}
+
+template <class T>
+static int launch_any(const Launch& l, cudaStream_t st) {
+#define X(N_, G_, R0, R1, R2, R3) \
+  if (l.fftN == N_) return launch_tma<T, Sched<N_, G_, R0, R1, R2, R3>>(l, st);
+#include ACCFFT_SCHEDULES_FILE
+#undef X
+  return -1;
+}
+#else
 template <class T>
 static int launch_any(const Launch& l, cudaStream_t st) {
 #define X(N_, G_, R0, R1, R2, R3) \
@@ -86,5 +207,6 @@ static int launch_any(const Launch& l, cudaStream_t st) {
 #undef X
   return -1;
 }
+#endif
 
 }  // namespace accfft_b200

@@ -55,6 +55,9 @@ struct StageDesc {
   int colShift;          // strided kernels: tiles start at column -colShift so that tile origins are line aligned
                          // in a destination whose rows this rank enters at an unaligned offset (inverse Y stage)
   int inv;               // 1: inverse transform (sign +1), done as swap(re,im) . forward . swap(re,im)
+  int staged;            // contiguous kernels with nseg > 1: outputs are collected in shared memory per destination
+                         // segment and leave the CTA as bulk (TMA) copies of whole runs -- full 128-byte lines on the
+                         // NVLink wire instead of one partial-line packet per warp store.  Set by the launcher.
 };
 
 template <class T>
@@ -197,6 +200,55 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
   }
 }
 
+// ---- staged (shared memory -> bulk copy) stores of the contiguous kernels ------------------------------------
+// Staging layout for a CTA of PC pencils and NOUT outputs per pencil:  [segment s][pencil][k - s*blk], i.e. element
+// (pencil, k) lives at  PC*s*blk + pencil*size_s + (k - s*blk)  with size_s = min(blk, NOUT - s*blk).  Rows of one
+// segment are adjacent, exactly like the destination buffer (dense rows of size_s elements, one per pencil), so the
+// PC pencils of a CTA form ONE contiguous run per destination rank whenever they share the outer index a.
+template <int PC>
+ACC_HD int staged_index(const StageDesc& d, int nout, int pcl, int k) {
+  const int s = seg_of(d, k);
+  const int rest = nout - s * d.blk;
+  const int size_s = rest < d.blk ? rest : d.blk;
+  return PC * s * d.blk + pcl * size_s + (k - s * d.blk);
+}
+
+// all threads of the CTA call this after their staged writes; idx0 = first pencil of the CTA
+template <class T, int PC, class Ctx>
+ACC_HD void staged_flush(const StageDesc& d, Ctx& ctx, const cplx<T>* stage, int nout, long long idx0, int nthreads) {
+  ctx.bulk_fence();
+  ctx.sync();
+  const long long total = (long long)d.nA * d.nB;
+  const int npen = (int)((total - idx0) < PC ? (total - idx0) : PC);
+  const int a0 = (int)(idx0 / d.nB), b0 = (int)(idx0 % d.nB);
+  const int tid = ctx.tid();
+  int issue = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    const int rest = nout - s * d.blk;
+    const int size_s = rest < d.blk ? rest : d.blk;
+    if (size_s <= 0) continue;
+    const SegDst& sd = d.seg[s];
+    const bool merged = (b0 + npen <= d.nB) && sd.strideB == size_s && sd.strideI == 1;
+    const int nruns = merged ? 1 : npen;
+    for (int r = 0; r < nruns; ++r) {
+      const long long idx = idx0 + r;
+      const int a = merged ? a0 : (int)(idx / d.nB), b = merged ? b0 : (int)(idx % d.nB);
+      cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
+      const cplx<T>* src = stage + PC * s * d.blk + r * size_s;
+      const int n = merged ? npen * size_s : size_s;
+      const unsigned bytes = (unsigned)n * (unsigned)sizeof(cplx<T>);
+      const bool aligned = sd.strideI == 1 && (((unsigned long long)dst | (unsigned long long)src | bytes) & 15ull) == 0;
+      if (aligned) {
+        if (tid == issue % nthreads) ctx.bulk_store(dst, src, bytes);
+        ++issue;
+      } else {
+        for (int i = tid; i < n; i += nthreads) dst[(long long)i * sd.strideI] = src[i];
+      }
+    }
+  }
+  ctx.bulk_wait();
+}
+
 // ================================================================================================
 // contiguous c2c: transform index has unit stride; PC pencils per CTA, G threads per pencil.
 // Used for the Z pass of c2c plans (reference fplan_0 of the c2c plan, src/accfft_gpu.cpp:767-790).
@@ -220,6 +272,7 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
     pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = cswap_if(in[i], inv); });
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
+  cplx<T>* stage = (cplx<T>*)ctx.smem() + ((PC * S::SMEM_ELEMS + 1) & ~1);   // only touched when d.staged
   fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
   if (valid) {
     if (stage_is_simple(d)) {
@@ -227,10 +280,13 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
       cplx<T>* out = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
       const long long so = sd.strideI;
       pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { out[(long long)k * so] = cswap_if(r, inv); });
+    } else if (d.staged) {
+      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { stage[staged_index<PC>(d, S::N, pcl, k)] = cswap_if(r, inv); });
     } else {
       pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, cswap_if(r, inv), k, a, b); });
     }
   }
+  if (d.staged) staged_flush<T, PC>(d, ctx, stage, S::N, ctx.bid() * PC, S::G * PC);
 }
 
 // ================================================================================================
@@ -263,6 +319,7 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  cplx<T>* stage = (cplx<T>*)ctx.smem() + ((PC * S::SMEM_ELEMS + 1) & ~1);   // only touched when d.staged
   // publish Z so every thread can read its mirror partner Z[M-k]
   if constexpr (S::NP > 1) ctx.sync();
   pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { sm[S::phys(k)] = r; });
@@ -275,6 +332,7 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
     const long long so = s0.strideI;
     auto put = [&](int kk, cplx<T> y) {
       if (simple) out0[(long long)kk * so] = y;
+      else if (d.staged) stage[staged_index<PC>(d, M + 1, pcl, kk)] = y;
       else store_generic(d, y, kk, a, b);
     };
     // split step X[k] = (E + W_N2^k O)/2 for k = j + r*NBL:  W_N2^k = W_N2^j * W_(2 RL)^r, the second factor a
@@ -302,6 +360,7 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
       }
     }
   }
+  if (d.staged) staged_flush<T, PC>(d, ctx, stage, M + 1, ctx.bid() * PC, S::G * PC);
 }
 
 // ================================================================================================

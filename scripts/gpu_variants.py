@@ -36,12 +36,20 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     torch.cuda.synchronize()
     prof = p.profile_read()
     err = float(torch.linalg.vector_norm(back / n**3 - x) / torch.linalg.vector_norm(x))
-    print(json.dumps({"lib": os.environ.get("ACCFFT_B200_LIB"), "n": n, "kind": kind, "single": single,
+    print(json.dumps({"lib": os.path.basename(os.environ.get("ACCFFT_B200_LIB", "")), "tma": os.environ.get("ACCFFT_B200_TMA", "1"), "n": n, "kind": kind, "single": single,
                       "ms_step": e0.elapsed_time(e1) / iters, "err": err,
                       "stages": {k: round(v[0] / max(v[1], 1), 4) for k, v in prof.items() if v[1]}}))
     sys.exit(0)
-for lib in sys.argv[1:]:
-    for kind, n, single in (("r2c", 512, "0"), ("c2c", 512, "0"), ("r2c", 256, "0"), ("r2c", 512, "1")):
+CASES = (("r2c", 512, "0"), ("c2c", 512, "0"), ("r2c", 256, "0"), ("r2c", 512, "1"))
+if os.environ.get("VAR_QUICK"):
+    CASES = CASES[:1]
+for spec in sys.argv[1:]:
+    # "path/to/lib.so" or "path/to/lib.so:ENV=VAL,ENV2=VAL2"
+    lib, _, extra = spec.partition(":")
+    for kind, n, single in CASES:
         env = dict(os.environ, ACCFFT_B200_LIB=os.path.abspath(lib), VAR_N=str(n), VAR_KIND=kind, VAR_SINGLE=single)
+        for kv in filter(None, extra.split(",")):
+            k, _, v = kv.partition("=")
+            env[k] = v
         r = subprocess.run([sys.executable, __file__, "--child"], env=env, capture_output=True, text=True, timeout=300)
         print(r.stdout.strip() or ("FAILED " + lib + " " + r.stderr[-400:]), flush=True)

@@ -71,13 +71,14 @@ for dims in GRIDS:
     check((64, 64, 64), dims, True, single=True)
 
 
-def bench(n, dims, r2c=True, iters=20):
+def bench(n, dims, r2c=True, iters=20, single=False):
     comm = acc.accfft_create_comm(list(dims))
-    p = acc.Plan(n, comm, r2c=r2c, single=False)
+    p = acc.Plan(n, comm, r2c=r2c, single=single)
     isz = p.isize
     cnt = isz[0] * isz[1] * isz[2] * (1 if r2c else 2)
-    x = torch.rand(cnt, dtype=torch.float64, device=dev)
-    out = torch.zeros(p.alloc_max // 8, dtype=torch.float64, device=dev)
+    rdt = torch.float32 if single else torch.float64
+    x = torch.rand(cnt, dtype=rdt, device=dev)
+    out = torch.zeros(p.alloc_max // (4 if single else 8), dtype=rdt, device=dev)
     back = torch.zeros_like(x)
     st = torch.cuda.Stream()
     p.set_stream(st.cuda_stream); p.set_blocking(False); p.set_profiling(True)
@@ -101,14 +102,36 @@ def bench(n, dims, r2c=True, iters=20):
     N = n[0] * n[1] * n[2]
     gf = 2 * 5 * N * np.log2(N) / (float(ms.item()) * 1e-3) / 1e9
     if rank == 0:
-        print(f"bench n={n} dims={dims} r2c={r2c}: {float(ms.item()):.3f} ms/round-trip  {gf:.0f} GFLOP/s  stages(ms/launch): " +
+        print(f"bench n={n} dims={dims} r2c={r2c} single={single}: {float(ms.item()):.3f} ms/round-trip  {gf:.0f} GFLOP/s  stages(ms/launch): " +
               " ".join(f"{k}={v[0]/max(v[1],1):.3f}" for k, v in prof.items()), flush=True)
+    if r2c and os.environ.get("MGPU_OPS", "1") == "1":
+        # operator timings (report as time, not GFLOP/s)
+        la = torch.zeros_like(x)
+        g = [torch.zeros_like(x) for _ in range(3)]
+        for name, fn in (("laplace", lambda: p.laplace(la, x)), ("grad", lambda: p.grad(g[0], g[1], g[2], x)),
+                         ("divergence", lambda: p.divergence(la, g[0], g[1], g[2]))):
+            with torch.cuda.stream(st):
+                fn()
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            with torch.cuda.stream(st):
+                e0.record(st)
+                for _ in range(5): fn()
+                e1.record(st)
+            torch.cuda.synchronize(); dist.barrier()
+            ms = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"   op {name}: {float(ms.item()):.3f} ms", flush=True)
     p.destroy()
 
 
 for dims in GRIDS[:2]:
     bench((512, 512, 512), dims, True)
     bench((512, 512, 512), dims, False)
+if world == 8:
+    bench((1024, 1024, 1024), (2, 4), True, single=True)
+    bench((768, 768, 384), (2, 4), True)
+    bench((256, 256, 256), (2, 4), True)
 if rank == 0:
     print("WORST", worst, "PASS" if worst <= 1e-12 else "FAIL", flush=True)
 dist.destroy_process_group()

@@ -88,6 +88,16 @@ struct EmuCtx {
   long long bid() const { return bid_; }
   void* smem() const { return smem_; }
   void sync() const { fiber_sync(); }
+  // bulk copies: same 16-byte rules as cp.async.bulk, enforced here so the emulator catches misuse
+  void bulk_fence() const {}
+  void bulk_store(void* gdst, const void* ssrc, unsigned bytes) const {
+    if (((uintptr_t)gdst | (uintptr_t)ssrc | bytes) & 15u) {
+      fprintf(stderr, "emul: misaligned bulk copy\n");
+      abort();
+    }
+    memcpy(gdst, ssrc, bytes);
+  }
+  void bulk_wait() const {}
 };
 
 template <class Body>
@@ -118,12 +128,16 @@ static void emu_launch_sched(const Launch& l) {
     }
     case K_CONTIG_C2C: {
       const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2c_body<T, S, C::PC>(d, c); });
+      StageDesc ds = d;
+      ds.staged = (d.nseg > 1 && d.op == OP_NONE && d.accumulate == 0) ? 1 : 0;
+      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_STAGED_SMEM, [&](EmuCtx& c) { contig_c2c_body<T, S, C::PC>(ds, c); });
       break;
     }
     case K_CONTIG_R2C: {
       const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_r2c_body<T, S, C::PC>(d, c); });
+      StageDesc ds = d;
+      ds.staged = (d.nseg > 1 && d.op == OP_NONE && d.accumulate == 0) ? 1 : 0;
+      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_STAGED_SMEM, [&](EmuCtx& c) { contig_r2c_body<T, S, C::PC>(ds, c); });
       break;
     }
     case K_CONTIG_C2R: {
