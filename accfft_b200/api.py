@@ -72,6 +72,7 @@ def lib():
     L.accfftb_plan_set_blocking.argtypes = [c_vp, c_int]
     L.accfftb_plan_set_profiling.argtypes = [c_vp, c_int]
     L.accfftb_plan_profile_read.argtypes = [c_vp, c_dp, ctypes.POINTER(c_ll)]
+    L.accfftb_plan_stage_variant.argtypes = [c_vp, c_int]
     L.accfftb_plan_alloc_max.restype = c_ll
     L.accfftb_plan_alloc_max.argtypes = [c_vp]
     L.accfftb_plan_launch_count.restype = c_ll
@@ -198,9 +199,11 @@ def _ptr(t) -> int:
 
 
 class Plan:
-    """accfft_plan_gpu / accfft_plan_gpuf."""
+    """accfft_plan_gpu / accfft_plan_gpuf.  flags defaults to ACCFFT_MEASURE like the reference
+    (include/accfft_gpu.h:103): plan creation times the two strided-stage kernels on plan-owned scratch and keeps the
+    faster one per stage; ACCFFT_ESTIMATE skips the timing and uses a size heuristic."""
 
-    def __init__(self, n, comm: Comm, r2c: bool, single: bool, flags: int = ACCFFT_ESTIMATE, wire: bool = True):
+    def __init__(self, n, comm: Comm, r2c: bool, single: bool, flags: int = ACCFFT_MEASURE, wire: bool = True):
         self.n, self.comm, self.r2c, self.single = tuple(int(x) for x in n), comm, r2c, single
         self._local_group = None
         L = lib()
@@ -238,6 +241,11 @@ class Plan:
         cnt = (ctypes.c_longlong * 7)()
         _check(lib().accfftb_plan_profile_read(self._h, ms, cnt), "profile_read")
         return {name: (ms[i], int(cnt[i])) for i, name in enumerate(self.PROFILE_SLOTS)}
+
+    def stage_kernels(self):
+        """-> {stage: "plain" | "tma" | "heuristic"} for the four strided stages (see accfftb_plan_stage_variant)"""
+        names = {0: "heuristic", 1: "plain", 2: "tma"}
+        return {self.PROFILE_SLOTS[s]: names.get(lib().accfftb_plan_stage_variant(self._h, s), "?") for s in (1, 2, 3, 4)}
 
     @property
     def launch_count(self) -> int:
@@ -331,17 +339,17 @@ def attach_local_peers(plans: Sequence[Plan]):
         p._local_group = list(plans)
 
 
-def accfft_plan_dft_3d_r2c_gpu(n, comm: Comm, flags: int = ACCFFT_ESTIMATE) -> Plan:
+def accfft_plan_dft_3d_r2c_gpu(n, comm: Comm, flags: int = ACCFFT_MEASURE) -> Plan:
     return Plan(n, comm, r2c=True, single=False, flags=flags)
 
 
-def accfft_plan_dft_3d_r2c_gpuf(n, comm: Comm, flags: int = ACCFFT_ESTIMATE) -> Plan:
+def accfft_plan_dft_3d_r2c_gpuf(n, comm: Comm, flags: int = ACCFFT_MEASURE) -> Plan:
     return Plan(n, comm, r2c=True, single=True, flags=flags)
 
 
-def accfft_plan_dft_3d_c2c_gpu(n, comm: Comm, flags: int = ACCFFT_ESTIMATE) -> Plan:
+def accfft_plan_dft_3d_c2c_gpu(n, comm: Comm, flags: int = ACCFFT_MEASURE) -> Plan:
     return Plan(n, comm, r2c=False, single=False, flags=flags)
 
 
-def accfft_plan_dft_3d_c2c_gpuf(n, comm: Comm, flags: int = ACCFFT_ESTIMATE) -> Plan:
+def accfft_plan_dft_3d_c2c_gpuf(n, comm: Comm, flags: int = ACCFFT_MEASURE) -> Plan:
     return Plan(n, comm, r2c=False, single=True, flags=flags)

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <string>
@@ -117,6 +118,7 @@ struct Engine {
   int rank = 0;
   cudaStream_t stream = 0;
   bool blocking = true;
+  int tma_mode = 1;            // ACCFFT_B200_TMA: 0 = never use the TMA stage kernel, 1 = tuned / heuristic, 2 = always
   bool wired = false;          // peers attached (always true for single-rank plans)
   char* slab = nullptr;        // [A | B | flags] of this rank
   size_t slab_bytes = 0, bufsz = 0;
@@ -126,6 +128,7 @@ struct Engine {
   std::vector<unsigned long long*> flag_ptrs;
   unsigned long long epoch = 0;
   long long launches = 0;
+  int variant[ACCFFTB_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0, 0};   // per stage slot: 0 heuristic, 1 plain, 2 TMA (set by autotune)
   std::map<std::pair<int, int>, void*> tables;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   // timing of the current call
@@ -221,14 +224,21 @@ int CudaBackend::launch(const Launch& l) {
   const int sel = (int)l.kind * 2 + (int)l.prec;
   switch (sel) {
     case 0:
-      // dry (plan-time) launches load BOTH variants; at run time the TMA kernel declines (-2) what it cannot take
-      rc = accfft_launch_k4_p0(l, e->stream);
-      if (rc == -2 || (l.dry && rc == 0)) rc = accfft_launch_k0_p0(l, e->stream);
+    case 1: {
+      // Two kernels serve the strided stages: the plain one and the TMA-pipelined persistent one.  Choice: the launch's
+      // own request, else what plan-time tuning (ACCFFT_MEASURE) found for this stage, else a heuristic from the
+      // measurements in profiles/variants_r05.txt (TMA wins when the tile's rows are a few KB apart -- the Y passes --
+      // and for single precision; the plain kernel wins on the plane-strided X passes in double).
+      // Dry (plan-time) launches load BOTH; at run time the TMA kernel declines (-2) what it cannot take.
+      int v = l.variant ? l.variant : e->variant[l.slot >= 0 && l.slot < ACCFFTB_PROFILE_SLOTS ? l.slot : 6];
+      if (v == 0) v = (l.desc.nA > 1 || l.prec == PREC_FLOAT) ? 2 : 1;
+      if (e->tma_mode == 0) v = 1;
+      if (e->tma_mode == 2) v = 2;
+      rc = -2;
+      if (v == 2 || l.dry) rc = sel == 0 ? accfft_launch_k4_p0(l, e->stream) : accfft_launch_k4_p1(l, e->stream);
+      if (rc == -2 || (l.dry && rc == 0)) rc = sel == 0 ? accfft_launch_k0_p0(l, e->stream) : accfft_launch_k0_p1(l, e->stream);
       break;
-    case 1:
-      rc = accfft_launch_k4_p1(l, e->stream);
-      if (rc == -2 || (l.dry && rc == 0)) rc = accfft_launch_k0_p1(l, e->stream);
-      break;
+    }
     case 2: rc = accfft_launch_k1_p0(l, e->stream); break;
     case 3: rc = accfft_launch_k1_p1(l, e->stream); break;
     case 4: rc = accfft_launch_k2_p0(l, e->stream); break;
@@ -335,6 +345,57 @@ struct TimerScope {
   }
 };
 
+// Plan-time tuning (ACCFFT_MEASURE / ACCFFT_PATIENT; the reference tunes its transpose method the same way,
+// src/transpose_gpu.cpp:632-743, but on the caller's buffers -- here only plan-owned scratch is touched).
+// Each strided stage is timed with both kernels on this rank's own input buffer, storing to a scratch array.
+static int autotune(Engine* e) {
+  Plan& pl = e->plan;
+  void* scratch = nullptr;
+  CU(cudaMalloc(&scratch, e->bufsz));
+  CU(cudaMemsetAsync(e->slab, 0, 2 * e->bufsz, e->stream));
+  Launch ls[4] = {pl.fwd_y(), pl.fwd_x(scratch), pl.inv_x(e->slab), pl.inv_y()};
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  int rc = 0;
+  for (Launch& l : ls) {
+    StageDesc& d = l.desc;
+    if (d.nA <= 0 || d.nB <= 0) continue;
+    // single local destination [a][k][b]: same bytes as the stage input, which fits one exchange buffer
+    d.nseg = 1;
+    d.blk = l.fftN;
+    d.seg[0].base = scratch;
+    d.seg[0].strideA = (long long)l.fftN * d.nB;
+    d.seg[0].strideB = 1;
+    d.seg[0].strideI = d.nB;
+    d.colShift = 0;
+    float best[3] = {0, 1e30f, 1e30f};
+    for (int v = 1; v <= 2 && !rc; ++v) {
+      l.variant = v;
+      for (int it = 0; it < 4 && !rc; ++it) {   // first iteration = warm-up
+        cudaEventRecord(a, e->stream);
+        rc = e->be.launch(l);
+        cudaEventRecord(b, e->stream);
+        if (rc) break;
+        cudaError_t err = cudaEventSynchronize(b);
+        if (err != cudaSuccess) rc = cuda_fail(err, "autotune");
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (it > 0 && ms < best[v]) best[v] = ms;
+      }
+    }
+    if (rc) break;
+    e->variant[l.slot] = best[2] < best[1] ? 2 : 1;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaMemsetAsync(e->slab, 0, 2 * e->bufsz, e->stream);
+  cudaStreamSynchronize(e->stream);
+  cudaFree(scratch);
+  e->launches = 0;
+  return rc;
+}
+
 }  // namespace accfft_b200
 
 using namespace accfft_b200;
@@ -411,7 +472,6 @@ int accfftb_stage_size(const int n[3], const int c_dims[2], const int coords[2],
 int accfftb_length_supported(int n) { return length_supported(n) ? 1 : 0; }
 
 accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank, int kind, int prec, unsigned flags) {
-  (void)flags;   // ESTIMATE / MEASURE / PATIENT: there is a single exchange method, nothing to tune
   if (!n || !c_dims || n[0] <= 0 || n[1] <= 0 || n[2] <= 0 || c_dims[0] <= 0 || c_dims[1] <= 0 || rank < 0 ||
       rank >= c_dims[0] * c_dims[1] || (kind != ACCFFTB_R2C && kind != ACCFFTB_C2C) ||
       (prec != ACCFFTB_DOUBLE && prec != ACCFFTB_FLOAT)) {
@@ -468,6 +528,9 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
     cudaFuncAttributes fa;
     err = cudaFuncGetAttributes(&fa, k_barrier);
     int rc = err == cudaSuccess ? pl.prepare() : (int)err;
+    if (const char* m = getenv("ACCFFT_B200_TMA")) e->tma_mode = m[0] == '0' ? 0 : m[0] == '2' ? 2 : 1;
+    // ACCFFT_MEASURE / ACCFFT_PATIENT: pick the faster kernel per strided stage by timing both (plan-owned buffers only)
+    if (!rc && (flags & (ACCFFTB_MEASURE | ACCFFTB_PATIENT)) && e->tma_mode == 1) rc = autotune(e);
     if (rc) {
       if (err != cudaSuccess) cuda_fail(err, "accfftb_plan_create (kernel load)");
       engine_free(e);
@@ -571,6 +634,11 @@ int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOT
   }
   e->recs.clear();
   return 0;
+}
+
+int accfftb_plan_stage_variant(const accfftb_plan* plan, int slot) {
+  if (!plan || slot < 0 || slot >= ACCFFTB_PROFILE_SLOTS) return -1;
+  return plan->e.variant[slot];
 }
 
 long long accfftb_plan_alloc_max(const accfftb_plan* plan) { return plan ? plan->e.plan.g.L.alloc_max : -1; }

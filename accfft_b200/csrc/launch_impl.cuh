@@ -128,13 +128,6 @@ static EncodeTiledFn encode_tiled_fn() {
   }();
   return fn;
 }
-static bool tma_enabled() {
-  static const int on = [] {
-    const char* e = getenv("ACCFFT_B200_TMA");
-    return (e && e[0] == '0') ? 0 : 1;
-  }();
-  return on != 0;
-}
 static int sm_count() {
   static thread_local int dev_cached = -1, sms = 0;
   int dev = 0;
@@ -165,7 +158,7 @@ static int launch_tma(const Launch& l, cudaStream_t st) {
     }
     constexpr long long es = C::ES;
     EncodeTiledFn enc = encode_tiled_fn();
-    if (!tma_enabled() || !enc || d.inStrideB != 1 || ((uintptr_t)d.in & 15) || (d.inStrideI * es) % 16 != 0 ||
+    if (!enc || d.inStrideB != 1 || ((uintptr_t)d.in & 15) || (d.inStrideI * es) % 16 != 0 ||
         (d.nA > 1 && (d.inStrideA * es) % 16 != 0) || d.inStrideI * es >= (1LL << 40) || d.inStrideA * es >= (1LL << 40))
       return -2;
     const int tpa = (d.nB + d.colShift + C0::TC - 1) / C0::TC;

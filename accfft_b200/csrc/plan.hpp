@@ -22,6 +22,7 @@ struct Launch {
   bool inverse;
   bool dry;        // true: only load / configure the kernel (plan time), do not launch
   int slot;        // profiling slot: 0 fwd Z, 1 fwd Y, 2 fwd X, 3 inv X, 4 inv Y, 5 inv Z  (6 = barrier)
+  int variant;     // strided stages: 0 = backend's choice (plan-time tuning / heuristic), 1 = plain kernel, 2 = TMA-pipelined kernel
   StageDesc desc;
 };
 

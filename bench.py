@@ -331,6 +331,7 @@ def main():
                        ((R + 2 * C0) / 1e9), "round_trip_rel_l2": rt_err},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "stages": stages, "step_roofline": step_roof,
+            "stage_kernels": plan.stage_kernels(),
         }
         print(json.dumps(line), flush=True)
     plan.destroy()

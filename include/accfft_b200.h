@@ -85,7 +85,8 @@ int accfftb_length_supported(int n);
  * on the current device (the reference's Mem_Mgr_gpu owns three device + two pinned host buffers,
  * src/transpose_gpu.cpp:58-131) and the twiddle tables.  Unlike the reference, plan creation never
  * touches user data (ACCFFT_MEASURE clobbers data_out there, src/accfft_gpu.cpp:382-386) so no data
- * pointers are taken.  Returns NULL on failure (as the reference does, :187-191). */
+ * pointers are taken.  flags: ACCFFTB_ESTIMATE or ACCFFTB_MEASURE / ACCFFTB_PATIENT (see accfftb_plan_stage_variant).
+ * Returns NULL on failure (as the reference does, :187-191). */
 accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank, int kind, int prec, unsigned flags);
 
 /* Multi-GPU wiring (replaces MPI_Comm_split + the host-staged MPI_Alltoall[v] machinery of
@@ -113,6 +114,12 @@ int accfftb_plan_set_blocking(accfftb_plan* plan, int blocking);
 #define ACCFFTB_PROFILE_SLOTS 7
 int accfftb_plan_set_profiling(accfftb_plan* plan, int on);
 int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOTS], long long count[ACCFFTB_PROFILE_SLOTS]);
+
+/* Which kernel serves a strided stage (slot 1 forward Y, 2 forward X, 3 inverse X, 4 inverse Y): 1 = plain kernel,
+ * 2 = TMA-pipelined persistent kernel, 0 = decided per launch by the size heuristic (plans made with ACCFFTB_ESTIMATE).
+ * Plans made with ACCFFTB_MEASURE / ACCFFTB_PATIENT time both at creation -- on plan-owned scratch, never on user
+ * data (the reference's tuner, src/transpose_gpu.cpp:632-743, runs on the caller's buffers) -- and keep the faster. */
+int accfftb_plan_stage_variant(const accfftb_plan* plan, int slot);
 
 long long accfftb_plan_alloc_max(const accfftb_plan* plan);
 /* number of kernels the plan has launched so far (stage kernels + inter-GPU barrier kernels) */

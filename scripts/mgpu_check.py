@@ -104,7 +104,9 @@ def bench(n, dims, r2c=True, iters=20, single=False):
     if rank == 0:
         print(f"bench n={n} dims={dims} r2c={r2c} single={single}: {float(ms.item()):.3f} ms/round-trip  {gf:.0f} GFLOP/s  stages(ms/launch): " +
               " ".join(f"{k}={v[0]/max(v[1],1):.3f}" for k, v in prof.items()), flush=True)
-    if r2c and os.environ.get("MGPU_OPS", "1") == "1":
+    if rank == 0:
+        print("   stage kernels:", p.stage_kernels(), flush=True)
+    if r2c and os.environ.get("MGPU_OPS", "1") == "1" and dims in ((2, 4), (8, 1), (2, 1), (2, 2)):
         # operator timings (report as time, not GFLOP/s)
         la = torch.zeros_like(x)
         g = [torch.zeros_like(x) for _ in range(3)]
@@ -125,11 +127,14 @@ def bench(n, dims, r2c=True, iters=20, single=False):
     p.destroy()
 
 
-for dims in GRIDS[:2]:
+for dims in GRIDS + ([(1, 8)] if world == 8 else []):
     bench((512, 512, 512), dims, True)
+for dims in GRIDS[:2]:
     bench((512, 512, 512), dims, False)
 if world == 8:
     bench((1024, 1024, 1024), (2, 4), True, single=True)
+    bench((1024, 1024, 1024), (8, 1), True, single=True)
+    bench((768, 768, 384), (8, 1), True)
     bench((768, 768, 384), (2, 4), True)
     bench((256, 256, 256), (2, 4), True)
 if rank == 0:

@@ -51,16 +51,25 @@ def make_plan(n, r2c, single, comm=None, **kw):
     return acc.Plan(n, comm, r2c=r2c, single=single, **kw)
 
 
+@pytest.fixture(params=["tuned", "plain", "tma"])
+def stage_kernels(request, monkeypatch):
+    """The strided (Y / X) stages have two kernels: the plain one and the TMA-pipelined persistent one.  Run the
+    parity tests under plan-time tuning (ACCFFT_MEASURE, the reference's default flag), and with each kernel forced
+    (ACCFFT_B200_TMA is read when a plan is created)."""
+    monkeypatch.setenv("ACCFFT_B200_TMA", {"tuned": "1", "plain": "0", "tma": "2"}[request.param])
+    return acc.ACCFFT_MEASURE if request.param == "tuned" else acc.ACCFFT_ESTIMATE
+
+
 SIZES = [(8, 8, 8), (16, 12, 20), (2, 2, 2), (4, 6, 10), (5, 3, 8), (32, 48, 64), (64, 64, 64), (96, 80, 100),
          (128, 128, 128), (192, 160, 200), (24, 40, 768), (400, 20, 32), (12, 1024, 16), (2048, 8, 12)]
 
 
 @pytest.mark.parametrize("n", SIZES)
 @pytest.mark.parametrize("single", [False, True])
-def test_r2c_forward_and_c2r_against_oracle(cuda_device, n, single):
+def test_r2c_forward_and_c2r_against_oracle(cuda_device, n, single, stage_kernels):
     x = orc.synthetic_real(n, 20240607)
     X = orc.forward_r2c(x)
-    p = make_plan(n, True, single)
+    p = make_plan(n, True, single, flags=stage_kernels)
     xd = to_dev(x.astype(dtypes(single)[0]), cuda_device)
     out = alloc_out(p, single, cuda_device)
     p.execute_r2c(xd, out)
@@ -78,10 +87,10 @@ def test_r2c_forward_and_c2r_against_oracle(cuda_device, n, single):
 @pytest.mark.parametrize("n", [(8, 8, 8), (16, 12, 20), (6, 10, 5), (64, 64, 64), (48, 96, 40), (128, 128, 128),
                                (20, 24, 1024)])
 @pytest.mark.parametrize("single", [False, True])
-def test_c2c_against_oracle(cuda_device, n, single):
+def test_c2c_against_oracle(cuda_device, n, single, stage_kernels):
     z = orc.synthetic_complex(n, 20240609)
     Z = orc.forward_c2c(z)
-    p = make_plan(n, False, single)
+    p = make_plan(n, False, single, flags=stage_kernels)
     cdt = dtypes(single)[1]
     zd = to_dev(z.astype(cdt), cuda_device)
     out = torch_mod().zeros_like(zd)
@@ -381,7 +390,7 @@ MR_CASES = [((16, 12, 20), (1, 2), True), ((16, 12, 20), (2, 1), True), ((16, 12
 
 
 @pytest.mark.parametrize("n,dims,r2c", MR_CASES)
-def test_multirank_threads_on_one_gpu(cuda_device, n, dims, r2c):
+def test_multirank_threads_on_one_gpu(cuda_device, n, dims, r2c, stage_kernels):
     """The exchange path (peer-addressed stores fused into the stage kernels + the inter-GPU barrier kernel)
     with all ranks on cuda:0: uneven and empty pencils included.  Replaces what the reference can only test
     by running under mpirun on a real machine."""
@@ -390,7 +399,7 @@ def test_multirank_threads_on_one_gpu(cuda_device, n, dims, r2c):
     x = orc.synthetic_real(n, 31) if r2c else orc.synthetic_complex(n, 31)
     X = orc.forward_r2c(x) if r2c else orc.forward_c2c(x)
     comms = [acc.Comm(r, nprocs, dims) for r in range(nprocs)]
-    plans = [acc.Plan(n, comms[r], r2c=r2c, single=False, wire=False) for r in range(nprocs)]
+    plans = [acc.Plan(n, comms[r], r2c=r2c, single=False, wire=False, flags=stage_kernels) for r in range(nprocs)]
     acc.attach_local_peers(plans)
     streams = [torch.cuda.Stream() for _ in range(nprocs)]
     ins, outs, backs = [], [], []
