@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -96,6 +97,31 @@ __global__ void __launch_bounds__(32) k_barrier(const __grid_constant__ BarrierD
   }
   __syncwarp();
   __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage without a transform (partial-axis executes, xyz != 111): the same descriptor as the FFT stage, but every
+// element just moves to where the next layout wants it.  The reference does this with its transposes alone
+// (src/accfft_gpu.cpp:488-495: "else data_out_d = data_d" followed by T_plan_1->execute_gpu).
+template <class T>
+__global__ void __launch_bounds__(256) k_copy_stage(const __grid_constant__ StageDesc d, int N, int kFast) {
+  const long long total = (long long)d.nA * d.nB * N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const cplx<T>* in = (const cplx<T>*)d.in;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    int a, b, k;
+    if (kFast) {
+      k = (int)(idx % N);
+      b = (int)((idx / N) % d.nB);
+      a = (int)(idx / ((long long)N * d.nB));
+    } else {
+      b = (int)(idx % d.nB);
+      k = (int)((idx / d.nB) % N);
+      a = (int)(idx / ((long long)N * d.nB));
+    }
+    const cplx<T> v = in[(long long)a * d.inStrideA + (long long)b * d.inStrideB + (long long)k * d.inStrideI];
+    store_generic(d, v, k, a, b);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -221,6 +247,20 @@ int CudaBackend::launch(const Launch& l) {
   ScopedTimer tm(e, l.dry ? nullptr : &e->t_fft);
   ScopedProfile pf(e, l.dry ? -1 : l.slot);
   int rc = -1;
+  if (l.kind == K_COPY) {
+    cudaFuncAttributes fa;
+    if (l.dry) return (int)(l.prec == PREC_DOUBLE ? cudaFuncGetAttributes(&fa, k_copy_stage<double>)
+                                                  : cudaFuncGetAttributes(&fa, k_copy_stage<float>));
+    const long long total = (long long)l.desc.nA * l.desc.nB * l.fftN;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+    const int kfast = l.desc.inStrideI == 1 ? 1 : 0;
+    if (l.prec == PREC_DOUBLE) k_copy_stage<double><<<grid, 256, 0, e->stream>>>(l.desc, l.fftN, kfast);
+    else k_copy_stage<float><<<grid, 256, 0, e->stream>>>(l.desc, l.fftN, kfast);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return cuda_fail(err, "copy stage launch");
+    e->launches++;
+    return 0;
+  }
   const int sel = (int)l.kind * 2 + (int)l.prec;
   switch (sel) {
     case 0:
@@ -230,8 +270,10 @@ int CudaBackend::launch(const Launch& l) {
       // measurements in profiles/variants_r05.txt (TMA wins when the tile's rows are a few KB apart -- the Y passes --
       // and for single precision; the plain kernel wins on the plane-strided X passes in double).
       // Dry (plan-time) launches load BOTH; at run time the TMA kernel declines (-2) what it cannot take.
+      // Stages that store to peers are NVLink-bound and want as many storing threads as possible: plain kernel
+      // (profiles/mgpu8_r05.log: the one-CTA-per-SM TMA kernel lost 5-10 % there).
       int v = l.variant ? l.variant : e->variant[l.slot >= 0 && l.slot < ACCFFTB_PROFILE_SLOTS ? l.slot : 6];
-      if (v == 0) v = (l.desc.nA > 1 || l.prec == PREC_FLOAT) ? 2 : 1;
+      if (v == 0) v = (l.desc.nseg == 1 && (l.desc.nA > 1 || l.prec == PREC_FLOAT)) ? 2 : 1;
       if (e->tma_mode == 0) v = 1;
       if (e->tma_mode == 2) v = 2;
       rc = -2;
@@ -361,6 +403,10 @@ static int autotune(Engine* e) {
   for (Launch& l : ls) {
     StageDesc& d = l.desc;
     if (d.nA <= 0 || d.nB <= 0) continue;
+    if (d.nseg > 1) {   // stores to peers: NVLink-bound, not tunable on this rank alone -- see CudaBackend::launch
+      e->variant[l.slot] = 1;
+      continue;
+    }
     // single local destination [a][k][b]: same bytes as the stage input, which fits one exchange buffer
     d.nseg = 1;
     d.blk = l.fftN;
@@ -655,7 +701,10 @@ int accfftb_plan_destroy(accfftb_plan* plan) {
   if (!(plan)) return fail(ACCFFTB_ERR_ARG, "null plan");                                          \
   if ((plan)->e.plan.g.r2c != (want_r2c))                                                           \
     return fail(ACCFFTB_ERR_ARG, (want_r2c) ? "this call needs an r2c plan" : "this call needs a c2c plan"); \
-  if (xyz != 7) return fail(ACCFFTB_ERR_UNSUPPORTED, "partial-axis transforms (xyz != 111) are not implemented"); \
+  if (xyz < 0 || xyz > 7) return fail(ACCFFTB_ERR_ARG, "xyz must be a 3-bit mask (bit 2 = Z, bit 1 = Y, bit 0 = X)"); \
+  if ((want_r2c) && !(xyz & 4))                                                                      \
+    return fail(ACCFFTB_ERR_UNSUPPORTED, "r2c / c2r need the Z axis selected: the real <-> complex step lives there " \
+                                         "(the reference reinterprets the real rows as complex in that case)"); \
   if (!(plan)->e.wired) return fail(ACCFFTB_ERR_STATE, "multi-rank plan used before its peers were attached");
 
 int accfftb_execute_r2c(accfftb_plan* plan, const void* data, void* data_out, double* timer, int xyz) {
@@ -663,7 +712,7 @@ int accfftb_execute_r2c(accfftb_plan* plan, const void* data, void* data_out, do
   if (!data || !data_out) return fail(ACCFFTB_ERR_ARG, "null data pointer");
   Engine* e = &plan->e;
   TimerScope ts(e, timer, 5);
-  return engine_finish(e, e->plan.execute_forward(data, data_out, data == data_out));
+  return engine_finish(e, e->plan.execute_forward(data, data_out, data == data_out, xyz));
 }
 
 int accfftb_execute_c2r(accfftb_plan* plan, const void* data, void* data_out, double* timer, int xyz) {
@@ -671,7 +720,7 @@ int accfftb_execute_c2r(accfftb_plan* plan, const void* data, void* data_out, do
   if (!data || !data_out) return fail(ACCFFTB_ERR_ARG, "null data pointer");
   Engine* e = &plan->e;
   TimerScope ts(e, timer, 5);
-  return engine_finish(e, e->plan.execute_inverse(data, data_out, data == data_out));
+  return engine_finish(e, e->plan.execute_inverse(data, data_out, data == data_out, xyz));
 }
 
 int accfftb_execute_c2c(accfftb_plan* plan, int direction, const void* data, void* data_out, double* timer, int xyz) {
@@ -681,8 +730,8 @@ int accfftb_execute_c2c(accfftb_plan* plan, int direction, const void* data, voi
     return fail(ACCFFTB_ERR_ARG, "direction must be ACCFFTB_FORWARD or ACCFFTB_BACKWARD");
   Engine* e = &plan->e;
   TimerScope ts(e, timer, 5);
-  if (direction == ACCFFTB_FORWARD) return engine_finish(e, e->plan.execute_forward(data, data_out, false));
-  return engine_finish(e, e->plan.execute_inverse(data, data_out, false));
+  if (direction == ACCFFTB_FORWARD) return engine_finish(e, e->plan.execute_forward(data, data_out, false, xyz));
+  return engine_finish(e, e->plan.execute_inverse(data, data_out, false, xyz));
 }
 
 static int ensure_spec(Engine* e) {

@@ -158,7 +158,9 @@ static int launch_tma(const Launch& l, cudaStream_t st) {
     }
     constexpr long long es = C::ES;
     EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc || d.inStrideB != 1 || ((uintptr_t)d.in & 15) || (d.inStrideI * es) % 16 != 0 ||
+    // (every box must start on a 16-byte boundary in global memory: a column shift of an odd number of 8-byte
+    // elements would start the boxes of a single-precision tile 8 bytes off -- the TMA unit faults on that)
+    if (!enc || d.inStrideB != 1 || ((uintptr_t)d.in & 15) || (d.inStrideI * es) % 16 != 0 || (d.colShift * es) % 16 != 0 ||
         (d.nA > 1 && (d.inStrideA * es) % 16 != 0) || d.inStrideI * es >= (1LL << 40) || d.inStrideA * es >= (1LL << 40))
       return -2;
     const int tpa = (d.nB + d.colShift + C0::TC - 1) / C0::TC;

@@ -327,6 +327,7 @@ long long Plan::buffer_bytes(const int n[3], const int np[2], const int coords[2
   return std::max<long long>(m * cs, 16);
 }
 
+static void no_transform(Launch& l, int n_axis);
 static bool empty(const Launch& l) { return l.desc.nA <= 0 || l.desc.nB <= 0; }
 
 int Plan::prepare() {
@@ -335,31 +336,46 @@ int Plan::prepare() {
     l.dry = true;
     if (int rc = be->launch(l)) return rc;
   }
-  return 0;
+  Launch c = fwd_y();   // the no-transform stage of partial-axis executes
+  no_transform(c, g.n[1]);
+  c.dry = true;
+  return be->launch(c);
 }
 
-int Plan::execute_forward(const void* in, void* out, bool in_padded) {
+// a stage whose axis is not selected only re-lays the data out (pack-on-store without the transform)
+static void no_transform(Launch& l, int n_axis) {
+  l.kind = K_COPY;
+  l.fftN = n_axis;
+}
+
+int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
   int rc;
   Launch z = fwd_z(in, in_padded);
+  if (!(xyz & 4)) no_transform(z, g.n[2]);
   if (!empty(z) && (rc = be->launch(z))) return rc;
   if (nprocs > 1 && (rc = be->barrier())) return rc;
   Launch y = fwd_y();
+  if (!(xyz & 2)) no_transform(y, g.n[1]);
   if (!empty(y) && (rc = be->launch(y))) return rc;
   if (nprocs > 1 && (rc = be->barrier())) return rc;
   Launch x = fwd_x(out);
+  if (!(xyz & 1)) no_transform(x, g.n[0]);
   if (!empty(x) && (rc = be->launch(x))) return rc;
   return 0;
 }
 
-int Plan::execute_inverse(const void* in, void* out, bool out_padded) {
+int Plan::execute_inverse(const void* in, void* out, bool out_padded, int xyz) {
   int rc;
   Launch x = inv_x(in);
+  if (!(xyz & 1)) no_transform(x, g.n[0]);
   if (!empty(x) && (rc = be->launch(x))) return rc;
   if (nprocs > 1 && (rc = be->barrier())) return rc;
   Launch y = inv_y();
+  if (!(xyz & 2)) no_transform(y, g.n[1]);
   if (!empty(y) && (rc = be->launch(y))) return rc;
   if (nprocs > 1 && (rc = be->barrier())) return rc;
   Launch z = inv_z(out, out_padded);
+  if (!(xyz & 4)) no_transform(z, g.n[2]);
   if (!empty(z) && (rc = be->launch(z))) return rc;
   return 0;
 }

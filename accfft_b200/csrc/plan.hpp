@@ -85,8 +85,11 @@ struct Plan {
   // Load and configure every kernel the plan can launch (CUDA loads kernels lazily, and a first-use load may
   // synchronise the context -- which must not happen while another rank's barrier kernel is spinning).
   int prepare();
-  int execute_forward(const void* in, void* out, bool in_padded);
-  int execute_inverse(const void* in, void* out, bool out_padded);
+  // xyz: bit 2 = Z, bit 1 = Y, bit 0 = X (the std::bitset<3> of accfft_execute_gpu, src/accfft_gpu.cpp:477,499,527):
+  // an axis whose bit is clear is not transformed, but its stage still moves the data into the next layout, exactly
+  // as the reference always runs its transposes.  r2c / c2r need the Z bit (the real <-> complex step).
+  int execute_forward(const void* in, void* out, bool in_padded, int xyz = 7);
+  int execute_inverse(const void* in, void* out, bool out_padded, int xyz = 7);
   // fused forward -> spectral symbol -> inverse (laplace / biharmonic; src/operators_gpu.txx:280-334, :555-609)
   int execute_spectral(const void* in, void* out, int op, void* spec);
   // grad (src/operators_gpu.txx:72-278): one forward into `spec` (normalised), then per selected component

@@ -230,30 +230,52 @@ def main():
     ms_per_step = ms / args.steps
     value = 2 * flops_per_transform(n) / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: host buffers through the public (blocking) API ---------------------------------------------
+    # ---- e2e: HOST buffers in, HOST buffers out -------------------------------------------------------------
+    # Every step copies its input field from pinned host memory to the device, runs r2c + c2r through the public
+    # API and copies the round-trip field back to pinned host memory.  Steps are software-pipelined over two device
+    # buffer sets and three streams (H2D of step k+1 and D2H of step k-1 overlap the transforms of step k: PCIe is
+    # full duplex and the copy engines are independent), the way a streaming caller would drive the library; the
+    # timed region covers ALL copies and transforms of the e_steps steps and ends when the last result is on the host.
     e2e = None
     if not args.no_e2e:
-        plan.set_blocking(True)
+        e_steps = max(4, min(args.steps, 12))
         xh = torch.empty(x.shape, dtype=torch.float64).pin_memory()
         xh.copy_(x)
-        yh = torch.empty(back.shape, dtype=torch.float64).pin_memory()
-        e_steps = max(3, min(args.steps, 10))
+        yh = [torch.empty(back.shape, dtype=torch.float64).pin_memory() for _ in range(2)]
+        xd = [x, torch.empty_like(x)]
+        bd = [back, torch.empty_like(back)]
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]      # input k landed
+        ev_fft = [torch.cuda.Event() for _ in range(2)]     # transforms of step k done (input buffer free, result ready)
+        ev_out = [torch.cuda.Event() for _ in range(2)]     # result k on the host (result buffer free)
 
-        def e2e_step():
-            x.copy_(xh, non_blocking=True)
-            plan.execute_r2c(x, out)
-            plan.execute_c2r(out, back)
-            yh.copy_(back, non_blocking=True)
-            stream.synchronize()
+        def e2e_run(nsteps):
+            for k in range(nsteps):
+                j = k & 1
+                with torch.cuda.stream(s_in):
+                    if k >= 2:
+                        s_in.wait_event(ev_fft[j])
+                    xd[j].copy_(xh, non_blocking=True)
+                    ev_in[j].record(s_in)
+                with torch.cuda.stream(stream):
+                    stream.wait_event(ev_in[j])
+                    if k >= 2:
+                        stream.wait_event(ev_out[j])
+                    plan.execute_r2c(xd[j], out)
+                    plan.execute_c2r(out, bd[j])
+                    ev_fft[j].record(stream)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_fft[j])
+                    yh[j].copy_(bd[j], non_blocking=True)
+                    ev_out[j].record(s_out)
 
-        with torch.cuda.stream(stream):
-            e2e_step()
-            sync_all()
-            t0 = time.perf_counter()
-            ev0.record(stream)
-            for _ in range(e_steps):
-                e2e_step()
-            ev1.record(stream)
+        e2e_run(2)
+        sync_all()
+        ev0.record(stream)
+        s_in.wait_event(ev0)
+        e2e_run(e_steps)
+        stream.wait_stream(s_out)
+        ev1.record(stream)
         sync_all()
         e_ms = ev0.elapsed_time(ev1)
         if world > 1:
@@ -261,11 +283,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
         e_ms /= e_steps
-        ok = bool(torch.allclose(yh[:1000] / N, xh[:1000], atol=1e-12))
+        ok = all(bool(torch.allclose(h[:4096] / N, xh[:4096], atol=1e-12)) and
+                 bool(torch.allclose(h[-4096:] / N, xh[-4096:], atol=1e-12)) for h in yh) if n_in else True
+        if not ok:
+            raise SystemExit("e2e round trip does not reproduce the host input: refusing to report a number")
         e2e = {"value": 2 * flops_per_transform(n) / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
-               "h2d_bytes_per_step": int(xh.numel() * 8), "d2h_bytes_per_step": int(yh.numel() * 8),
-               "ms_per_step": e_ms, "steps": e_steps, "checked": ok}
-        plan.set_blocking(False)
+               "h2d_bytes_per_step": int(xh.numel() * 8), "d2h_bytes_per_step": int(yh[0].numel() * 8),
+               "ms_per_step": e_ms, "steps": e_steps, "checked": ok,
+               "how": "pinned host -> device -> r2c -> c2r -> pinned host every step; steps pipelined over 2 buffer sets / 3 streams"}
     clocks = sampler.result()
 
     # ---- roofline of the dominant stage kernel -----------------------------------------------------------

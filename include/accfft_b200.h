@@ -135,8 +135,10 @@ int accfftb_plan_destroy(accfftb_plan* plan);
  *   Pack and unpack are fused into the FFT kernels here, so [1] = [3] = 0 and [0] = [2] = time spent in
  *   the inter-GPU barriers; [4] = time in the stage kernels (which includes their NVLink stores).
  * xyz: bit 2 = Z, bit 1 = Y, bit 0 = X like the std::bitset<3> of the reference
- *   (src/accfft_gpu.cpp:477,499,527); only 7 (all axes) is implemented, anything else returns
- *   ACCFFTB_ERR_UNSUPPORTED.
+ *   (src/accfft_gpu.cpp:477,499,527).  An axis whose bit is clear is not transformed; its stage still moves the
+ *   data into the next layout (the reference always runs its transposes), so the output layout never changes.
+ *   r2c / c2r need bit 2: the real <-> complex step is the Z stage (the reference reinterprets the real rows as
+ *   complex when Z is deselected, which is not a transform) -- otherwise ACCFFTB_ERR_UNSUPPORTED.
  */
 
 /* accfft_execute_r2c_gpu / _gpuf (src/accfft_gpu.cpp:635-649): real [isize] (rows of N2 reals, or of

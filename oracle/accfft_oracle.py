@@ -173,6 +173,36 @@ def inverse_c2c(X: np.ndarray) -> np.ndarray:
     return np.fft.ifftn(X, axes=(0, 1, 2)) * X.size
 
 
+def _axes_of(xyz: int):
+    """bit 2 = Z (axis 2), bit 1 = Y (axis 1), bit 0 = X (axis 0): the std::bitset<3> xyz of
+    accfft_execute_gpu / accfft_execute_c2c_gpu (src/accfft_gpu.cpp:477,499,527; :975,1000,1029)."""
+    return [ax for ax, bit in ((0, 1), (1, 2), (2, 4)) if xyz & bit]
+
+
+def forward_partial(x: np.ndarray, xyz: int, r2c: bool) -> np.ndarray:
+    """Partial-axis forward transform: only the axes selected in xyz are transformed, the data still ends in the
+    output layout (the reference always runs its transposes).  r2c needs the Z bit (src/accfft_gpu.cpp:477-488)."""
+    if r2c:
+        assert xyz & 4
+        X = np.fft.rfft(np.asarray(x, dtype=np.float64), axis=2)
+        axes = [a for a in _axes_of(xyz) if a != 2]
+        return np.fft.fftn(X, axes=axes) if axes else X
+    axes = _axes_of(xyz)
+    z = np.asarray(x, dtype=np.complex128)
+    return np.fft.fftn(z, axes=axes) if axes else z.copy()
+
+
+def inverse_partial(X: np.ndarray, n, xyz: int, r2c: bool) -> np.ndarray:
+    """Unnormalised partial-axis inverse (mirror of forward_partial)."""
+    if r2c:
+        assert xyz & 4
+        axes = [a for a in _axes_of(xyz) if a != 2]
+        Y = np.fft.ifftn(X, axes=axes) * np.prod([n[a] for a in axes]) if axes else X
+        return np.fft.irfft(Y, n=n[2], axis=2) * n[2]
+    axes = _axes_of(xyz)
+    return np.fft.ifftn(X, axes=axes) * np.prod([n[a] for a in axes]) if axes else np.array(X, copy=True)
+
+
 def local_input(x: np.ndarray, n, np_, coords) -> np.ndarray:
     """Rank (c0,c1)'s input block x[istart0:+isize0, istart1:+isize1, :]  (steps/step1/step1.cpp:162-170)."""
     s0, st0 = block(n[0], np_[0], coords[0])

@@ -159,7 +159,23 @@ static bool emu_supported(int N) {
   return false;
 }
 
+// stage without a transform (partial-axis executes): same element walk as k_copy_stage in engine.cu
+template <class T>
+static void emu_copy_stage(const Launch& l) {
+  const StageDesc& d = l.desc;
+  const cplx<T>* in = (const cplx<T>*)d.in;
+  for (int a = 0; a < d.nA; ++a)
+    for (int b = 0; b < d.nB; ++b)
+      for (int k = 0; k < l.fftN; ++k)
+        store_generic(d, in[(long long)a * d.inStrideA + (long long)b * d.inStrideB + (long long)k * d.inStrideI], k, a, b);
+}
+
 static void emu_launch(const Launch& l) {
+  if (l.kind == K_COPY) {
+    if (l.prec == PREC_DOUBLE) emu_copy_stage<double>(l);
+    else emu_copy_stage<float>(l);
+    return;
+  }
 #define X(N_, G_, R0, R1, R2, R3)                                                       \
   if (l.fftN == N_) {                                                                   \
     if (l.prec == PREC_DOUBLE) emu_launch_sched<double, Sched<N_, G_, R0, R1, R2, R3>>(l); \
@@ -297,6 +313,22 @@ int emu_execute(void* h, int mode, void** in, void** out, int padded) {
       else rc[r] = p.execute_spectral(in[r], out[r], OP_BIHARMONIC, w->spec[r].data());
     });
   }
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w->nprocs; ++r)
+    if (rc[r]) return rc[r];
+  return canaries_ok(w) ? 0 : -99;
+}
+
+// partial-axis transforms: mode 0 forward, 1 inverse; xyz bit 2 = Z, bit 1 = Y, bit 0 = X
+int emu_execute_xyz(void* h, int mode, void** in, void** out, int xyz) {
+  EmuWorld* w = (EmuWorld*)h;
+  std::vector<std::thread> th;
+  std::vector<int> rc(w->nprocs, 0);
+  for (int r = 0; r < w->nprocs; ++r)
+    th.emplace_back([&, r]() {
+      Plan& p = w->plans[r];
+      rc[r] = mode == 0 ? p.execute_forward(in[r], out[r], false, xyz) : p.execute_inverse(in[r], out[r], false, xyz);
+    });
   for (auto& t : th) t.join();
   for (int r = 0; r < w->nprocs; ++r)
     if (rc[r]) return rc[r];

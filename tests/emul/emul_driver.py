@@ -48,6 +48,9 @@ def lib():
         _lib.emu_execute.restype = ctypes.c_int
         _lib.emu_execute.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
                                      ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
+        _lib.emu_execute_xyz.restype = ctypes.c_int
+        _lib.emu_execute_xyz.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                         ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         pp = ctypes.POINTER(ctypes.c_void_p)
         _lib.emu_execute_grad.restype = ctypes.c_int
         _lib.emu_execute_grad.argtypes = [ctypes.c_void_p, pp, pp, pp, pp, ctypes.c_int]
@@ -80,10 +83,13 @@ class World:
     def coords(self, r):
         return orc.rank_to_coords(r, self.np_)
 
-    def _run(self, mode, ins, outs, padded=False):
+    def _run(self, mode, ins, outs, padded=False, xyz=7):
         pin = (ctypes.c_void_p * self.nprocs)(*[a.ctypes.data for a in ins])
         pout = (ctypes.c_void_p * self.nprocs)(*[a.ctypes.data for a in outs])
-        rc = lib().emu_execute(self.h, mode, pin, pout, int(padded))
+        if xyz != 7:
+            rc = lib().emu_execute_xyz(self.h, mode, pin, pout, xyz)
+        else:
+            rc = lib().emu_execute(self.h, mode, pin, pout, int(padded))
         if rc:
             raise RuntimeError(f"emu_execute rc={rc}")
 
@@ -92,7 +98,7 @@ class World:
         return [np.zeros(lib().emu_alloc_max(self.h, r) // self.rdt().itemsize, dtype=self.rdt)
                 for r in range(self.nprocs)]
 
-    def forward(self, x_global, padded=False):
+    def forward(self, x_global, padded=False, xyz=7):
         n = self.n
         ins = []
         for r in range(self.nprocs):
@@ -108,7 +114,7 @@ class World:
                 loc = loc.astype(self.cdt)
             ins.append(np.ascontiguousarray(loc))
         outs = self.alloc_out()
-        self._run(0, ins, outs, padded)
+        self._run(0, ins, outs, padded, xyz)
         blocks = []
         n2c = n[2] // 2 + 1 if self.r2c else n[2]
         for r in range(self.nprocs):
@@ -119,14 +125,14 @@ class World:
             blocks.append(outs[r].view(self.cdt)[:cnt].reshape(n[0], s1, s2).copy())
         return blocks
 
-    def inverse(self, X_global, padded=False):
+    def inverse(self, X_global, padded=False, xyz=7):
         n = self.n
         ins = []
         for r in range(self.nprocs):
             loc = orc.local_output(X_global, n, self.np_, self.coords(r), r2c=self.r2c).astype(self.cdt)
             ins.append(np.ascontiguousarray(loc))
         outs = self.alloc_out()
-        self._run(1, ins, outs, padded)
+        self._run(1, ins, outs, padded, xyz)
         blocks = []
         for r in range(self.nprocs):
             c = self.coords(r)

@@ -63,11 +63,33 @@ def test_grad_divergence_all_ranks(n, np_):
     w.close()
 
 
-def test_single_precision():
-    n, np_ = (12, 10, 16), (2, 2)
+@pytest.mark.parametrize("n,np_", [((8, 8, 8), (1, 1)), ((12, 10, 16), (2, 2)), ((6, 12, 10), (3, 2))])
+@pytest.mark.parametrize("xyz", [0b100, 0b110, 0b101, 0b011, 0b010, 0b001, 0b000])
+def test_partial_axis_transforms(n, np_, xyz):
+    """std::bitset<3> xyz of accfft_execute_*: unselected axes are only re-laid out (src/accfft_gpu.cpp:477-539)"""
+    z = orc.synthetic_complex(n, 11)
+    w = emu.World(n, np_, r2c=False)
+    Z = orc.forward_partial(z, xyz, r2c=False)
+    assert orc.rel_l2(orc.assemble_output(w.forward(z, xyz=xyz), n, np_, r2c=False), Z) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.inverse(Z, xyz=xyz), n, np_), orc.inverse_partial(Z, n, xyz, False)) < 1e-12
+    w.close()
+    if xyz & 4:
+        x = orc.synthetic_real(n, 12)
+        w = emu.World(n, np_, r2c=True)
+        X = orc.forward_partial(x, xyz, r2c=True)
+        assert orc.rel_l2(orc.assemble_output(w.forward(x, xyz=xyz), n, np_), X) < 1e-12
+        assert orc.rel_l2(orc.assemble_input(w.inverse(X, xyz=xyz), n, np_), orc.inverse_partial(X, n, xyz, True)) < 1e-12
+        w.close()
+
+
+@pytest.mark.parametrize("n,np_", [((12, 10, 16), (2, 2)), ((12, 10, 20), (2, 4)), ((8, 32, 32), (1, 4))])
+def test_single_precision(n, np_):
+    # (2,4) / (1,4): odd spectral block sizes -> the staged Z-stage stores take their unaligned (element-wise) path
     x = orc.synthetic_real(n, 9)
     w = emu.World(n, np_, r2c=True, single=True)
-    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), orc.forward_r2c(x)) < 1e-5
+    X = orc.forward_r2c(x)
+    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), X) < 1e-5
+    assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, np_), x * x.size) < 1e-5
     w.close()
 
 

@@ -106,6 +106,40 @@ def test_c2c_against_oracle(cuda_device, n, single, stage_kernels):
     p.destroy()
 
 
+@pytest.mark.parametrize("xyz", [0b100, 0b110, 0b101, 0b011, 0b010, 0b001, 0b000])
+@pytest.mark.parametrize("n", [(16, 12, 20), (64, 48, 96)])
+def test_partial_axis_transforms(cuda_device, n, xyz):
+    """std::bitset<3> xyz of accfft_execute_{r2c,c2r,c2c}_gpu (src/accfft_gpu.cpp:477-539, :975-1029): only the selected
+    axes are transformed, the layout is always the output layout."""
+    torch = torch_mod()
+    z = orc.synthetic_complex(n, 77)
+    Z = orc.forward_partial(z, xyz, r2c=False)
+    p = make_plan(n, False, False)
+    zd = to_dev(z, cuda_device)
+    out = torch.zeros_like(zd)
+    p.execute_c2c(acc.ACCFFT_FORWARD, zd, out, xyz=xyz)
+    assert orc.rel_l2(out.cpu().numpy(), Z) <= 1e-12
+    back = torch.zeros_like(zd)
+    p.execute_c2c(acc.ACCFFT_BACKWARD, out, back, xyz=xyz)
+    assert orc.rel_l2(back.cpu().numpy(), orc.inverse_partial(Z, n, xyz, False)) <= 1e-12
+    p.destroy()
+    p = make_plan(n, True, False)
+    x = orc.synthetic_real(n, 78)
+    xd = to_dev(x, cuda_device)
+    out = alloc_out(p, False, cuda_device)
+    if xyz & 4:
+        X = orc.forward_partial(x, xyz, r2c=True)
+        p.execute_r2c(xd, out, xyz=xyz)
+        assert orc.rel_l2(spectrum(out, n, False), X) <= 1e-12
+        back = torch.zeros_like(xd)
+        p.execute_c2r(out, back, xyz=xyz)
+        assert orc.rel_l2(back.cpu().numpy(), orc.inverse_partial(X, n, xyz, True)) <= 1e-12
+    else:
+        with pytest.raises(acc.AccfftError):   # the real <-> complex step is the Z stage
+            p.execute_r2c(xd, out, xyz=xyz)
+    p.destroy()
+
+
 def test_golden_fixtures(cuda_device):
     files = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
     assert files
@@ -322,8 +356,10 @@ def test_error_behaviour(cuda_device):
     out = alloc_out(p, False, cuda_device)
     with pytest.raises(acc.AccfftError):     # wrong plan kind (the reference prints and returns, :641-646)
         p.execute_c2c(acc.ACCFFT_FORWARD, x, out)
-    with pytest.raises(acc.AccfftError):     # partial-axis transforms are not implemented
-        p.execute_r2c(x, out, xyz=0b100)
+    with pytest.raises(acc.AccfftError):     # r2c without the Z axis is not a transform (see accfft_b200.h)
+        p.execute_r2c(x, out, xyz=0b011)
+    with pytest.raises(acc.AccfftError):     # not a 3-bit mask
+        p.execute_r2c(x, out, xyz=8)
     with pytest.raises(acc.AccfftError):
         p.execute_r2c(None, out)
     with pytest.raises(acc.AccfftError):     # host tensor
@@ -387,27 +423,34 @@ MR_CASES = [((16, 12, 20), (1, 2), True), ((16, 12, 20), (2, 1), True), ((16, 12
             ((12, 10, 16), (2, 2), True), ((5, 6, 6), (2, 2), True), ((64, 48, 40), (2, 2), True),
             ((3, 5, 4), (4, 1), True), ((16, 12, 20), (2, 2), False), ((6, 10, 5), (1, 4), False),
             ((128, 128, 128), (2, 2), True)]
+# single precision: blocks of 5,5,5,2 / 9,9,9,6 spectral columns -- odd and even row strides in one process grid, i.e.
+# ranks that can and ranks that cannot use the TMA stage kernel side by side, and unaligned column shifts
+MR_CASES_F = [((8, 32, 32), (1, 4), True), ((8, 32, 32), (2, 4), True), ((16, 64, 64), (2, 4), True),
+              ((32, 32, 12), (2, 2), False), ((64, 64, 64), (2, 2), True)]
 
 
-@pytest.mark.parametrize("n,dims,r2c", MR_CASES)
-def test_multirank_threads_on_one_gpu(cuda_device, n, dims, r2c, stage_kernels):
+@pytest.mark.parametrize("n,dims,r2c,single", [c + (False,) for c in MR_CASES] + [c + (True,) for c in MR_CASES_F])
+def test_multirank_threads_on_one_gpu(cuda_device, n, dims, r2c, single, stage_kernels):
     """The exchange path (peer-addressed stores fused into the stage kernels + the inter-GPU barrier kernel)
     with all ranks on cuda:0: uneven and empty pencils included.  Replaces what the reference can only test
     by running under mpirun on a real machine."""
     torch = torch_mod()
     nprocs = dims[0] * dims[1]
+    rdt, cdt = dtypes(single)
+    tdt = torch.float32 if single else torch.float64
+    es = 4 if single else 8
     x = orc.synthetic_real(n, 31) if r2c else orc.synthetic_complex(n, 31)
     X = orc.forward_r2c(x) if r2c else orc.forward_c2c(x)
     comms = [acc.Comm(r, nprocs, dims) for r in range(nprocs)]
-    plans = [acc.Plan(n, comms[r], r2c=r2c, single=False, wire=False, flags=stage_kernels) for r in range(nprocs)]
+    plans = [acc.Plan(n, comms[r], r2c=r2c, single=single, wire=False, flags=stage_kernels) for r in range(nprocs)]
     acc.attach_local_peers(plans)
     streams = [torch.cuda.Stream() for _ in range(nprocs)]
     ins, outs, backs = [], [], []
     for r in range(nprocs):
-        loc = orc.local_input(x, n, dims, comms[r].coords)
-        t = to_dev(loc, cuda_device) if loc.size else torch.zeros(1, dtype=torch.float64, device=cuda_device)
-        ins.append(t.view(torch.float64) if not r2c else t)
-        outs.append(torch.zeros(max(plans[r].alloc_max // 8, 2), dtype=torch.float64, device=cuda_device))
+        loc = orc.local_input(x, n, dims, comms[r].coords).astype(rdt if r2c else cdt)
+        t = to_dev(loc, cuda_device) if loc.size else torch.zeros(2, dtype=tdt, device=cuda_device)
+        ins.append(torch.view_as_real(t).contiguous() if (not r2c and loc.size) else t)
+        outs.append(torch.zeros(max(plans[r].alloc_max // es, 2), dtype=tdt, device=cuda_device))
         backs.append(torch.zeros_like(ins[-1]))
         plans[r].set_stream(streams[r].cuda_stream)
     torch.cuda.synchronize()
@@ -428,16 +471,16 @@ def test_multirank_threads_on_one_gpu(cuda_device, n, dims, r2c, stage_kernels):
     for r in range(nprocs):
         osz = plans[r].osize
         cnt = osz[0] * osz[1] * osz[2]
-        blocks.append(outs[r].cpu().numpy().view(np.complex128)[:cnt].reshape(osz))
-    assert orc.rel_l2(orc.assemble_output(blocks, n, dims, r2c=r2c), X) <= 1e-12
+        blocks.append(outs[r].cpu().numpy().view(cdt)[:cnt].reshape(osz))
+    assert orc.rel_l2(orc.assemble_output(blocks, n, dims, r2c=r2c), X) <= TOL[single]
     bl = []
     for r in range(nprocs):
         isz = plans[r].isize
         cnt = isz[0] * isz[1] * isz[2]
-        b = backs[r].cpu().numpy()
-        b = b.view(np.complex128) if not r2c else b
-        bl.append(b.ravel()[:cnt].reshape(isz))
-    assert orc.rel_l2(orc.assemble_input(bl, n, dims), x * x.size) <= 1e-12
+        b = backs[r].cpu().numpy().ravel()
+        b = b.view(cdt) if not r2c else b
+        bl.append(b[:cnt].reshape(isz))
+    assert orc.rel_l2(orc.assemble_input(bl, n, dims), x * x.size) <= TOL[single]
     for p in plans:
         acc.lib().accfftb_plan_destroy(p._h)
         p._h = None
