@@ -85,6 +85,10 @@ def lib():
     L.accfftb_biharmonic.argtypes = [c_vp, c_vp, c_vp, c_dp]
     L.accfftb_grad.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dp]
     L.accfftb_divergence.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_dp]
+    L.accfftb_grad_slow.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dp]
+    L.accfftb_divergence_slow.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_dp]
+    L.accfftb_execute_r2c_axis.argtypes = [c_vp, c_int, c_vp, c_vp, c_dp]
+    L.accfftb_execute_c2r_axis.argtypes = [c_vp, c_int, c_vp, c_vp, c_dp]
     _LIB = L
     return L
 
@@ -233,12 +237,12 @@ class Plan:
     def set_profiling(self, on: bool):
         _check(lib().accfftb_plan_set_profiling(self._h, int(on)), "set_profiling")
 
-    PROFILE_SLOTS = ("fwd_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "inv_z", "barrier")
+    PROFILE_SLOTS = ("fwd_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "inv_z", "barrier", "axis_copy", "axis_fft")
 
     def profile_read(self):
         """-> {slot name: (total ms, launches)} since the last read (synchronises the plan's stream)"""
-        ms = (ctypes.c_double * 7)()
-        cnt = (ctypes.c_longlong * 7)()
+        ms = (ctypes.c_double * len(self.PROFILE_SLOTS))()
+        cnt = (ctypes.c_longlong * len(self.PROFILE_SLOTS))()
         _check(lib().accfftb_plan_profile_read(self._h, ms, cnt), "profile_read")
         return {name: (ms[i], int(cnt[i])) for i, name in enumerate(self.PROFILE_SLOTS)}
 
@@ -281,6 +285,36 @@ class Plan:
                "accfft_execute_c2c_gpu")
         self._timer_back(arr, timer)
 
+    # ---- single-axis real transforms (accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t, src/accfft_gpu.cpp:1212-1604) -------
+    AXES = {"x": 0, "y": 1, "z": 2}
+
+    def axis_size(self, axis):
+        """-> (size, start) of this rank's block of the single-axis half spectrum (osize_xi / osize_yi / osize_0)"""
+        axis = self.AXES.get(axis, axis)
+        which = {0: 6, 1: 4, 2: 0}[axis]
+        size, start = (ctypes.c_int * 3)(), (ctypes.c_int * 3)()
+        _check(lib().accfftb_stage_size(_i3(self.n), _i2(self.comm.c_dims), _i2(self.comm.coords), _R2C,
+                                        4 if self.single else 8, which, size, start), "accfftb_stage_size")
+        if axis == 1:   # starts of the y path: ostart_y (which = 3)
+            s3 = (ctypes.c_int * 3)()
+            _check(lib().accfftb_stage_size(_i3(self.n), _i2(self.comm.c_dims), _i2(self.comm.coords), _R2C,
+                                            4 if self.single else 8, 3, s3, start), "accfftb_stage_size")
+        return tuple(size), tuple(start)
+
+    def execute_r2c_axis(self, axis, data, data_out, timer=None):
+        """accfft_execute_r2c_{x,y,z}_gpu_t(plan, data, data_out, timer): axis = 0/1/2 or "x"/"y"/"z" """
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_execute_r2c_axis(self._h, self.AXES.get(axis, axis), _ptr(data), _ptr(data_out), p),
+               "accfft_execute_r2c_axis")
+        self._timer_back(arr, timer)
+
+    def execute_c2r_axis(self, axis, data, data_out, timer=None):
+        """accfft_execute_c2r_{x,y,z}_gpu_t(plan, data, data_out, timer)"""
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_execute_c2r_axis(self._h, self.AXES.get(axis, axis), _ptr(data), _ptr(data_out), p),
+               "accfft_execute_c2r_axis")
+        self._timer_back(arr, timer)
+
     # ---- spectral operators (accfft_operators_gpu.h) ---------------------------------------------
     def laplace(self, LA, A, timer=None):
         """accfft_laplace_gpu(LA, A, plan, timer)"""
@@ -304,6 +338,19 @@ class Plan:
         """accfft_divergence_gpu(div, Ax, Ay, Az, plan, timer)"""
         arr, p = self._timer(timer)
         _check(lib().accfftb_divergence(self._h, _ptr(Ax), _ptr(Ay), _ptr(Az), _ptr(div), p), "accfft_divergence_gpu")
+        self._timer_back(arr, timer)
+
+    def grad_slow(self, Ax, Ay, Az, A, xyz: int = 0b111, timer=None):
+        """accfft_grad_gpu_slow_t (src/operators_gpu.txx:72-170): full 3-D transforms instead of per-axis ones"""
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_grad_slow(self._h, _ptr(A), _ptr(Ax), _ptr(Ay), _ptr(Az), xyz, p), "accfft_grad_slow_gpu")
+        self._timer_back(arr, timer)
+
+    def divergence_slow(self, div, Ax, Ay, Az, timer=None):
+        """accfft_divergence_slow_gpu (src/operators_gpu.txx:336-446)"""
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_divergence_slow(self._h, _ptr(Ax), _ptr(Ay), _ptr(Az), _ptr(div), p),
+               "accfft_divergence_slow_gpu")
         self._timer_back(arr, timer)
 
     # ---- teardown --------------------------------------------------------------------------------

@@ -153,6 +153,22 @@ void exec_c2c(Plan* p, int direction, Cplx* data, Cplx* out, double* timer, std:
   report(p->procid, "accfft_execute_c2c_gpu", accfftb_execute_c2c(p->impl, direction, data, out, timer, bits(xyz)));
 }
 
+// single-axis real transforms: accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t (src/accfft_gpu.cpp:1212-1604)
+template <typename Plan, typename Real, typename Cplx>
+void exec_r2c_axis(Plan* p, int axis, Real* data, Cplx* out, double* timer) {
+  if (!baked(p, true, "accfft_execute_r2c_{x,y,z}_gpu_t")) return;
+  if (!data) data = p->data;
+  if (!out) out = (Cplx*)p->data_out;
+  report(p->procid, "accfft_execute_r2c_{x,y,z}_gpu_t", accfftb_execute_r2c_axis(p->impl, axis, data, out, timer));
+}
+template <typename Plan, typename Real, typename Cplx>
+void exec_c2r_axis(Plan* p, int axis, Cplx* data, Real* out, double* timer) {
+  if (!baked(p, true, "accfft_execute_c2r_{x,y,z}_gpu_t")) return;
+  if (!data) data = (Cplx*)p->data_out;
+  if (!out) out = p->data;
+  report(p->procid, "accfft_execute_c2r_{x,y,z}_gpu_t", accfftb_execute_c2r_axis(p->impl, axis, data, out, timer));
+}
+
 }  // namespace
 
 // ---- common ---------------------------------------------------------------------------------------------------
@@ -255,6 +271,36 @@ void accfft_execute_c2r_gpu_t(accfft_plan_gpu* plan, Tc* data, T* data_out, doub
 }
 template void accfft_execute_r2c_gpu_t<double, Complex>(accfft_plan_gpu*, double*, Complex*, double*, std::bitset<3>);
 template void accfft_execute_c2r_gpu_t<Complex, double>(accfft_plan_gpu*, Complex*, double*, double*, std::bitset<3>);
+template <typename T, typename Tc>
+void accfft_execute_r2c_z_gpu_t(accfft_plan_gpu* plan, T* data, Tc* data_out, double* timer) {
+  exec_r2c_axis(plan, 2, data, data_out, timer);
+}
+template <typename Tc, typename T>
+void accfft_execute_c2r_z_gpu_t(accfft_plan_gpu* plan, Tc* data, T* data_out, double* timer) {
+  exec_c2r_axis(plan, 2, data, data_out, timer);
+}
+template void accfft_execute_r2c_z_gpu_t<double, Complex>(accfft_plan_gpu*, double*, Complex*, double*);
+template void accfft_execute_c2r_z_gpu_t<Complex, double>(accfft_plan_gpu*, Complex*, double*, double*);
+template <typename T, typename Tc>
+void accfft_execute_r2c_y_gpu_t(accfft_plan_gpu* plan, T* data, Tc* data_out, double* timer) {
+  exec_r2c_axis(plan, 1, data, data_out, timer);
+}
+template <typename Tc, typename T>
+void accfft_execute_c2r_y_gpu_t(accfft_plan_gpu* plan, Tc* data, T* data_out, double* timer) {
+  exec_c2r_axis(plan, 1, data, data_out, timer);
+}
+template void accfft_execute_r2c_y_gpu_t<double, Complex>(accfft_plan_gpu*, double*, Complex*, double*);
+template void accfft_execute_c2r_y_gpu_t<Complex, double>(accfft_plan_gpu*, Complex*, double*, double*);
+template <typename T, typename Tc>
+void accfft_execute_r2c_x_gpu_t(accfft_plan_gpu* plan, T* data, Tc* data_out, double* timer) {
+  exec_r2c_axis(plan, 0, data, data_out, timer);
+}
+template <typename Tc, typename T>
+void accfft_execute_c2r_x_gpu_t(accfft_plan_gpu* plan, Tc* data, T* data_out, double* timer) {
+  exec_c2r_axis(plan, 0, data, data_out, timer);
+}
+template void accfft_execute_r2c_x_gpu_t<double, Complex>(accfft_plan_gpu*, double*, Complex*, double*);
+template void accfft_execute_c2r_x_gpu_t<Complex, double>(accfft_plan_gpu*, Complex*, double*, double*);
 
 // ---- single precision -----------------------------------------------------------------------------------------
 int dfft_get_local_size_gpuf(int N0, int N1, int N2, int* isize, int* istart, MPI_Comm c_comm) {
@@ -301,10 +347,40 @@ void accfft_execute_c2r_gpu_t(accfft_plan_gpuf* plan, Tc* data, T* data_out, dou
 }
 template void accfft_execute_r2c_gpu_t<float, Complexf>(accfft_plan_gpuf*, float*, Complexf*, double*, std::bitset<3>);
 template void accfft_execute_c2r_gpu_t<Complexf, float>(accfft_plan_gpuf*, Complexf*, float*, double*, std::bitset<3>);
+template <typename T, typename Tc>
+void accfft_execute_r2c_z_gpu_t(accfft_plan_gpuf* plan, T* data, Tc* data_out, double* timer) {
+  exec_r2c_axis(plan, 2, data, data_out, timer);
+}
+template <typename Tc, typename T>
+void accfft_execute_c2r_z_gpu_t(accfft_plan_gpuf* plan, Tc* data, T* data_out, double* timer) {
+  exec_c2r_axis(plan, 2, data, data_out, timer);
+}
+template void accfft_execute_r2c_z_gpu_t<float, Complexf>(accfft_plan_gpuf*, float*, Complexf*, double*);
+template void accfft_execute_c2r_z_gpu_t<Complexf, float>(accfft_plan_gpuf*, Complexf*, float*, double*);
+template <typename T, typename Tc>
+void accfft_execute_r2c_y_gpu_t(accfft_plan_gpuf* plan, T* data, Tc* data_out, double* timer) {
+  exec_r2c_axis(plan, 1, data, data_out, timer);
+}
+template <typename Tc, typename T>
+void accfft_execute_c2r_y_gpu_t(accfft_plan_gpuf* plan, Tc* data, T* data_out, double* timer) {
+  exec_c2r_axis(plan, 1, data, data_out, timer);
+}
+template void accfft_execute_r2c_y_gpu_t<float, Complexf>(accfft_plan_gpuf*, float*, Complexf*, double*);
+template void accfft_execute_c2r_y_gpu_t<Complexf, float>(accfft_plan_gpuf*, Complexf*, float*, double*);
+template <typename T, typename Tc>
+void accfft_execute_r2c_x_gpu_t(accfft_plan_gpuf* plan, T* data, Tc* data_out, double* timer) {
+  exec_r2c_axis(plan, 0, data, data_out, timer);
+}
+template <typename Tc, typename T>
+void accfft_execute_c2r_x_gpu_t(accfft_plan_gpuf* plan, Tc* data, T* data_out, double* timer) {
+  exec_c2r_axis(plan, 0, data, data_out, timer);
+}
+template void accfft_execute_r2c_x_gpu_t<float, Complexf>(accfft_plan_gpuf*, float*, Complexf*, double*);
+template void accfft_execute_c2r_x_gpu_t<Complexf, float>(accfft_plan_gpuf*, Complexf*, float*, double*);
 
 // ---- spectral operators ------------------------------------------------------------------------------------------
-// The reference offers a "fast" (per-axis transforms) and a "slow" (full 3-D transforms) variant of grad and divergence
-// with identical results; here both names reach the same fused implementation (symbol multiply inside the X stage).
+// The reference offers a "fast" (per-axis transforms, src/operators_gpu.txx:172-278) and a "slow" (full 3-D transforms,
+// :72-170) variant of grad and divergence with identical results; both exist here (accfftb_grad / accfftb_grad_slow).
 template <typename T, typename Tp>
 void accfft_grad_gpu_t(T* A_x, T* A_y, T* A_z, T* A, Tp* plan, std::bitset<3>* pXYZ, double* timer) {
   if (!baked(plan, true, "accfft_grad_gpu")) return;
@@ -313,7 +389,9 @@ void accfft_grad_gpu_t(T* A_x, T* A_y, T* A_z, T* A, Tp* plan, std::bitset<3>* p
 }
 template <typename T, typename Tp>
 void accfft_grad_gpu_slow_t(T* A_x, T* A_y, T* A_z, T* A, Tp* plan, std::bitset<3>* pXYZ, double* timer) {
-  accfft_grad_gpu_t(A_x, A_y, A_z, A, plan, pXYZ, timer);
+  if (!baked(plan, true, "accfft_grad_gpu_slow")) return;
+  const int comps = pXYZ ? bits(*pXYZ) : 7;
+  report(plan->procid, "accfft_grad_gpu_slow", accfftb_grad_slow(plan->impl, A, A_x, A_y, A_z, comps, timer));
 }
 template <typename T, typename Tp>
 void accfft_laplace_gpu_t(T* LA, T* A, Tp* plan, double* timer) {
@@ -327,7 +405,8 @@ void accfft_divergence_gpu_t(T* divA, T* A_x, T* A_y, T* A_z, Tp* plan, double* 
 }
 template <typename T, typename Tp>
 void accfft_divergence_gpu_slow_t(T* divA, T* A_x, T* A_y, T* A_z, Tp* plan, double* timer) {
-  accfft_divergence_gpu_t(divA, A_x, A_y, A_z, plan, timer);
+  if (!baked(plan, true, "accfft_divergence_slow_gpu")) return;
+  report(plan->procid, "accfft_divergence_slow_gpu", accfftb_divergence_slow(plan->impl, A_x, A_y, A_z, divA, timer));
 }
 template <typename T, typename Tp>
 void accfft_biharmonic_gpu_t(T* LA, T* A, Tp* plan, double* timer) {

@@ -32,6 +32,12 @@ int accfft_launch_k2_p1(const Launch&, cudaStream_t);
 int accfft_launch_k3_p1(const Launch&, cudaStream_t);
 int accfft_launch_k4_p0(const Launch&, cudaStream_t);   // TMA-pipelined strided stage; -2 = does not qualify
 int accfft_launch_k4_p1(const Launch&, cudaStream_t);
+int accfft_launch_k5_p0(const Launch&, cudaStream_t);   // strided r2c / c2r / derivative (stage_real.cuh)
+int accfft_launch_k5_p1(const Launch&, cudaStream_t);
+int accfft_launch_k6_p0(const Launch&, cudaStream_t);
+int accfft_launch_k6_p1(const Launch&, cudaStream_t);
+int accfft_launch_k7_p0(const Launch&, cudaStream_t);
+int accfft_launch_k7_p1(const Launch&, cudaStream_t);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -124,6 +130,17 @@ __global__ void __launch_bounds__(256) k_copy_stage(const __grid_constant__ Stag
   }
 }
 
+// Real copy stage of the single-axis paths (stage_real.cuh: copy_real_element): the reference's real-data transposes
+// T_plan_y / T_plan_x (+ inverses) and the cudaMemcpy D2D around them (src/accfft_gpu.cpp:1357-1362, :1404-1409,
+// :1509-1511, :1541-1545) as ONE gather/scatter whose stores land in the owning rank's buffer.
+template <class T>
+__global__ void __launch_bounds__(256) k_copy_real(const __grid_constant__ StageDesc d, long long nK) {
+  const long long total = (long long)d.nA * d.nB * nK;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
+    copy_real_element<T>(d, idx, nK);
+}
+
 // ---------------------------------------------------------------------------------------------------
 struct Engine;
 struct CudaBackend : Backend {
@@ -154,7 +171,7 @@ struct Engine {
   std::vector<unsigned long long*> flag_ptrs;
   unsigned long long epoch = 0;
   long long launches = 0;
-  int variant[ACCFFTB_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0, 0};   // per stage slot: 0 heuristic, 1 plain, 2 TMA (set by autotune)
+  int variant[ACCFFTB_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per stage slot: 0 heuristic, 1 plain, 2 TMA (set by autotune)
   std::map<std::pair<int, int>, void*> tables;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   // timing of the current call
@@ -243,7 +260,7 @@ struct ScopedTimer {
 };
 
 int CudaBackend::launch(const Launch& l) {
-  if (!l.desc.tw) return fail(ACCFFTB_ERR_STATE, "twiddle table allocation failed");
+  if (!l.desc.tw && l.kind != K_COPY_REAL) return fail(ACCFFTB_ERR_STATE, "twiddle table allocation failed");
   ScopedTimer tm(e, l.dry ? nullptr : &e->t_fft);
   ScopedProfile pf(e, l.dry ? -1 : l.slot);
   int rc = -1;
@@ -258,6 +275,19 @@ int CudaBackend::launch(const Launch& l) {
     else k_copy_stage<float><<<grid, 256, 0, e->stream>>>(l.desc, l.fftN, kfast);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return cuda_fail(err, "copy stage launch");
+    e->launches++;
+    return 0;
+  }
+  if (l.kind == K_COPY_REAL) {
+    cudaFuncAttributes fa;
+    if (l.dry) return (int)(l.prec == PREC_DOUBLE ? cudaFuncGetAttributes(&fa, k_copy_real<double>)
+                                                  : cudaFuncGetAttributes(&fa, k_copy_real<float>));
+    const long long total = (long long)l.desc.nA * l.desc.nB * l.copyN;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+    if (l.prec == PREC_DOUBLE) k_copy_real<double><<<grid, 256, 0, e->stream>>>(l.desc, l.copyN);
+    else k_copy_real<float><<<grid, 256, 0, e->stream>>>(l.desc, l.copyN);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return cuda_fail(err, "real copy stage launch");
     e->launches++;
     return 0;
   }
@@ -287,6 +317,12 @@ int CudaBackend::launch(const Launch& l) {
     case 5: rc = accfft_launch_k2_p1(l, e->stream); break;
     case 6: rc = accfft_launch_k3_p0(l, e->stream); break;
     case 7: rc = accfft_launch_k3_p1(l, e->stream); break;
+    case 10: rc = accfft_launch_k5_p0(l, e->stream); break;
+    case 11: rc = accfft_launch_k5_p1(l, e->stream); break;
+    case 12: rc = accfft_launch_k6_p0(l, e->stream); break;
+    case 13: rc = accfft_launch_k6_p1(l, e->stream); break;
+    case 14: rc = accfft_launch_k7_p0(l, e->stream); break;
+    case 15: rc = accfft_launch_k7_p1(l, e->stream); break;
     default: break;
   }
   if (rc == -1) return fail(ACCFFTB_ERR_UNSUPPORTED, "no kernel schedule for length " + std::to_string(l.fftN));
@@ -761,10 +797,11 @@ int accfftb_biharmonic(accfftb_plan* plan, const void* A, void* BA, double* time
   return engine_finish(e, e->plan.execute_spectral(A, BA, OP_BIHARMONIC, e->spec));
 }
 
-int accfftb_grad(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int comps, double* timer) {
+static int grad_impl(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int comps, double* timer, bool slow) {
   const int xyz = 7;
   CHECK_PLAN(plan, true);
   if (!A) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  if (comps < 0 || comps > 7) return fail(ACCFFTB_ERR_ARG, "component mask must be 0..7");
   if (((comps & 1) && !Ax) || ((comps & 2) && !Ay) || ((comps & 4) && !Az))
     return fail(ACCFFTB_ERR_ARG, "selected gradient component has a null output pointer");
   Engine* e = &plan->e;
@@ -772,19 +809,55 @@ int accfftb_grad(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az
   if (rc) return rc;
   TimerScope ts(e, timer, 7);
   void* outs[3] = {Ax, Ay, Az};
-  return engine_finish(e, e->plan.execute_grad(A, outs, comps, e->spec));
+  return engine_finish(e, slow ? e->plan.execute_grad(A, outs, comps, e->spec) : e->plan.execute_grad_axes(A, outs, comps, e->spec));
 }
 
-int accfftb_divergence(accfftb_plan* plan, const void* Ax, const void* Ay, const void* Az, void* div, double* timer) {
+static int div_impl(accfftb_plan* plan, const void* Ax, const void* Ay, const void* Az, void* div, double* timer, bool slow) {
   const int xyz = 7;
   CHECK_PLAN(plan, true);
   if (!Ax || !Ay || !Az || !div) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  if (!slow && (div == Ay || div == Az)) return fail(ACCFFTB_ERR_ARG, "divergence output must not alias an input component");
   Engine* e = &plan->e;
   int rc = ensure_spec(e);
   if (rc) return rc;
   TimerScope ts(e, timer, 7);
   const void* ins[3] = {Ax, Ay, Az};
-  return engine_finish(e, e->plan.execute_divergence(ins, div, e->spec));
+  return engine_finish(e, slow ? e->plan.execute_divergence(ins, div, e->spec) : e->plan.execute_divergence_axes(ins, div, e->spec));
+}
+
+int accfftb_grad(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int comps, double* timer) {
+  return grad_impl(plan, A, Ax, Ay, Az, comps, timer, false);
+}
+int accfftb_grad_slow(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int comps, double* timer) {
+  return grad_impl(plan, A, Ax, Ay, Az, comps, timer, true);
+}
+int accfftb_divergence(accfftb_plan* plan, const void* Ax, const void* Ay, const void* Az, void* div, double* timer) {
+  return div_impl(plan, Ax, Ay, Az, div, timer, false);
+}
+int accfftb_divergence_slow(accfftb_plan* plan, const void* Ax, const void* Ay, const void* Az, void* div, double* timer) {
+  return div_impl(plan, Ax, Ay, Az, div, timer, true);
+}
+
+int accfftb_execute_r2c_axis(accfftb_plan* plan, int axis, const void* data, void* data_out, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, true);
+  if (axis < 0 || axis > 2) return fail(ACCFFTB_ERR_ARG, "axis must be 0 (x), 1 (y) or 2 (z)");
+  if (!data || !data_out) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  if (data == data_out) return fail(ACCFFTB_ERR_UNSUPPORTED, "single-axis transforms are out of place");
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 5);
+  return engine_finish(e, e->plan.execute_r2c_axis(axis, data, data_out));
+}
+
+int accfftb_execute_c2r_axis(accfftb_plan* plan, int axis, const void* data, void* data_out, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, true);
+  if (axis < 0 || axis > 2) return fail(ACCFFTB_ERR_ARG, "axis must be 0 (x), 1 (y) or 2 (z)");
+  if (!data || !data_out) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  if (data == data_out) return fail(ACCFFTB_ERR_UNSUPPORTED, "single-axis transforms are out of place");
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 5);
+  return engine_finish(e, e->plan.execute_c2r_axis(axis, data, data_out));
 }
 
 }  // extern "C"

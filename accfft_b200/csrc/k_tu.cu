@@ -1,7 +1,8 @@
 // k_tu.cu -- compiled once per (ACCFFT_KIND, ACCFFT_PREC) pair (see Makefile): instantiates the stage
 // kernels of that kind / precision for every schedule and exports one launcher.
 //   ACCFFT_KIND: 0 strided c2c (Y and X passes), 1 contiguous c2c (Z pass of c2c plans),
-//                2 contiguous r2c, 3 contiguous c2r (Z pass of r2c plans)
+//                2 contiguous r2c, 3 contiguous c2r (Z pass of r2c plans), 4 TMA-pipelined strided c2c,
+//                5 strided r2c, 6 strided c2r, 7 strided spectral derivative (single-axis real paths, stage_real.cuh)
 //   ACCFFT_PREC: 0 double, 1 float
 #include "launch_impl.cuh"
 

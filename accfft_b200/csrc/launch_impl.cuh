@@ -54,6 +54,26 @@ __global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_c2r(const 
   contig_c2r_body<T, S, Cfg<T, S>::PC>(d, ctx);
 }
 
+#ifndef ACCFFT_REAL_MINB
+#define ACCFFT_REAL_MINB 2   // two 512-thread CTAs per SM (<= 64 registers): measured 25 % faster than one (profiles/op_bench_r07.txt)
+#endif
+// real transforms along a strided axis (stage_real.cuh): same CTA shape as k_strided_c2c, a tile = 2*TC real columns
+template <class T, class S>
+__global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS, ACCFFT_REAL_MINB) k_strided_r2c(const __grid_constant__ StageDesc d) {
+  CudaCtx ctx;
+  strided_r2c_body<T, S, Cfg<T, S>::TC>(d, ctx);
+}
+template <class T, class S>
+__global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS, ACCFFT_REAL_MINB) k_strided_c2r(const __grid_constant__ StageDesc d) {
+  CudaCtx ctx;
+  strided_c2r_body<T, S, Cfg<T, S>::TC>(d, ctx);
+}
+template <class T, class S>
+__global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS, ACCFFT_REAL_MINB) k_strided_deriv(const __grid_constant__ StageDesc d) {
+  CudaCtx ctx;
+  strided_deriv_body<T, S, Cfg<T, S>::TC>(d, ctx);
+}
+
 template <class K>
 static int launch_kernel(K kernel, long long nblocks, int threads, int smem, const StageDesc& d, cudaStream_t st,
                          bool dry) {
@@ -97,6 +117,15 @@ static int launch_one(const Launch& l, cudaStream_t st) {
 #if ACCFFT_KIND == 0
   const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
   return launch_kernel(k_strided_c2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
+#elif ACCFFT_KIND >= 5
+  const long long nb = (long long)d.nA * ((d.nB + 2 * C::TC - 1) / (2 * C::TC));
+#if ACCFFT_KIND == 5
+  return launch_kernel(k_strided_r2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
+#elif ACCFFT_KIND == 6
+  return launch_kernel(k_strided_c2r<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
+#else
+  return launch_kernel(k_strided_deriv<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
+#endif
 #elif ACCFFT_KIND == 1
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
   return launch_kernel(k_contig_c2c<T, S>, nb, C::CONTIG_THREADS, contig_smem, d, st, l.dry);

@@ -22,6 +22,9 @@ Geometry make_geometry(const int n[3], const int np[2], const int coords[2], boo
   g.i1 = block_of(n[1], np[1], coords[1]);
   g.k2 = block_of(g.n2c, np[1], coords[1]);
   g.k1 = block_of(n[1], np[0], coords[0]);
+  g.n2b = block_of(n[2], np[1], coords[1]);
+  g.M = (long long)g.i1.size * n[2];
+  g.mb = block_of((int)g.M, np[0], coords[0]);
   g.L = r2c ? local_size_r2c(n, np, coords, sizeofReal) : local_size_c2c(n, np, coords, sizeofReal);
   return g;
 }
@@ -323,12 +326,22 @@ long long Plan::buffer_bytes(const int n[3], const int np[2], const int coords[2
   const long long a = (long long)i0.size * n[1] * k2.size;
   const long long b1 = (long long)n[0] * k1.size * tmp.pitch(k2.size);
   const long long b2 = (long long)i0.size * i1.size * tmp.pitch(n2c);
-  const long long m = std::max(a, std::max(b1, b2));
-  return std::max<long long>(m * cs, 16);
+  long long m = std::max(a, std::max(b1, b2)) * cs;
+  if (r2c) {
+    // single-axis real paths: [i0][N1][n2b] and [N0][mb] reals in A (the physical layout [i0][i1][N2] in B is covered by b2)
+    const long long rs = cs / 2;
+    const Blk n2b = block_of(n[2], np[1], coords[1]);
+    const Blk mb = block_of((int)((long long)i1.size * n[2]), np[0], coords[0]);
+    m = std::max(m, (long long)i0.size * n[1] * n2b.size * rs);
+    m = std::max(m, (long long)n[0] * mb.size * rs);
+  }
+  return std::max<long long>(m, 16);
 }
 
 static void no_transform(Launch& l, int n_axis);
-static bool empty(const Launch& l) { return l.desc.nA <= 0 || l.desc.nB <= 0; }
+static bool empty(const Launch& l) {
+  return l.desc.nA <= 0 || l.desc.nB <= 0 || (l.kind == K_COPY_REAL && l.copyN <= 0);
+}
 
 int Plan::prepare() {
   Launch ls[6] = {fwd_z(nullptr, false), fwd_y(), fwd_x(nullptr), inv_x(nullptr), inv_y(), inv_z(nullptr, false)};
@@ -339,7 +352,19 @@ int Plan::prepare() {
   Launch c = fwd_y();   // the no-transform stage of partial-axis executes
   no_transform(c, g.n[1]);
   c.dry = true;
-  return be->launch(c);
+  if (int rc = be->launch(c)) return rc;
+  if (g.r2c) {
+    for (int axis = 0; axis < 2; ++axis)
+      for (int mode = 0; mode < 3; ++mode) {
+        Launch a = ax_stage(axis, mode, nullptr, nullptr);
+        a.dry = true;
+        if (int rc = be->launch(a)) return rc;
+      }
+    Launch ci = ax_copy_out(nullptr);
+    ci.dry = true;
+    if (int rc = be->launch(ci)) return rc;
+  }
+  return 0;
 }
 
 // a stage whose axis is not selected only re-lays the data out (pack-on-store without the transform)
@@ -461,6 +486,260 @@ int Plan::execute_divergence(const void* const ins[3], void* out, void* spec) {
   if (nprocs > 1 && (rc = be->barrier())) return rc;
   Launch zi = inv_z(out, false);
   if (!empty(zi) && (rc = be->launch(zi))) return rc;
+  return 0;
+}
+
+// ================================================================================================================
+// single-axis real transforms (reference: accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t, src/accfft_gpu.cpp:1212-1604) and the
+// per-axis spectral derivative built from them (src/operators_gpu.txx:172-278).
+//   y: real [i0][i1][N2] --row group, N2 split--> [i0][N1][n2b]  -> spectrum [i0][N1/2+1][n2b]      (osize_y / osize_yi)
+//   x: real [i0][M = i1*N2] --column group, M split--> [N0][mb]  -> spectrum [N0/2+1][mb]           (osize_x / osize_xi)
+//   z: local, spectrum [i0][i1][N2c]                                                                  (osize_0)
+// Buffer discipline (same invariant as the 3-D path, section 3 of DESIGN.md): peers' A may be written at any time but is
+// never read after the LAST barrier of an operation; peers' B is never written before the FIRST barrier of an operation.
+// ================================================================================================================
+Launch Plan::ax_copy_in(int axis, const void* in) const {
+  Launch l{};
+  const size_t rs = prec == PREC_DOUBLE ? 8 : 4;
+  StageDesc d = blank();
+  d.in = in;
+  d.nA = g.i0.size;
+  d.inStrideI = 1;
+  if (axis == 1) {
+    const int P1 = g.np[1];
+    d.nB = g.i1.size;
+    d.inStrideA = (long long)g.i1.size * g.n[2];
+    d.inStrideB = g.n[2];
+    l.copyN = g.n[2];
+    set_segs_common(d, P1, ceil_blk(g.n[2], P1));
+    for (int p = 0; p < P1; ++p) {
+      const Blk n2p = block_of(g.n[2], P1, p);
+      const int r = rank_of(g.np, g.coords[0], p);
+      d.seg[p].base = offs(peerA[r], (long long)g.i1.start * n2p.size, rs);
+      d.seg[p].strideA = (long long)g.n[1] * n2p.size;
+      d.seg[p].strideB = n2p.size;
+      d.seg[p].strideI = 1;
+    }
+  } else {
+    const int P0 = g.np[0];
+    d.nB = g.M > 0 ? 1 : 0;
+    d.inStrideA = g.M;
+    d.inStrideB = 0;
+    l.copyN = g.M;
+    set_segs_common(d, P0, std::max(1, ceil_blk((int)g.M, P0)));
+    for (int q = 0; q < P0; ++q) {
+      const Blk mq = block_of((int)g.M, P0, q);
+      const int r = rank_of(g.np, q, g.coords[1]);
+      d.seg[q].base = offs(peerA[r], (long long)g.i0.start * mq.size, rs);
+      d.seg[q].strideA = mq.size;
+      d.seg[q].strideB = 0;
+      d.seg[q].strideI = 1;
+    }
+  }
+  l.kind = K_COPY_REAL;
+  l.prec = prec;
+  l.desc = d;
+  l.slot = 7;
+  return l;
+}
+
+Launch Plan::ax_copy_out(void* out) const {
+  Launch l{};
+  StageDesc d = blank();
+  const int self = rank_of(g.np, g.coords[0], g.coords[1]);
+  d.in = peerB.empty() ? nullptr : peerB[self];
+  d.nA = g.i0.size;
+  d.nB = g.i1.size;
+  d.inStrideA = (long long)g.i1.size * g.n[2];
+  d.inStrideB = g.n[2];
+  d.inStrideI = 1;
+  l.copyN = g.n[2];
+  set_segs_common(d, 1, g.n[2]);
+  d.seg[0].base = out;
+  d.seg[0].strideA = d.inStrideA;
+  d.seg[0].strideB = d.inStrideB;
+  d.seg[0].strideI = 1;
+  l.kind = K_COPY_REAL;
+  l.prec = prec;
+  l.desc = d;
+  l.slot = 7;
+  return l;
+}
+
+Launch Plan::ax_stage(int axis, int mode, const void* in, void* out) const {
+  Launch l{};
+  const size_t rs = prec == PREC_DOUBLE ? 8 : 4;
+  StageDesc d = blank();
+  const int self = rank_of(g.np, g.coords[0], g.coords[1]);
+  const int N = g.n[axis];
+  const bool ex = ax_exchanges(axis);
+  const long long cols = axis == 1 ? (ex ? g.n2b.size : g.n[2]) : (ex ? (long long)g.mb.size : g.M);
+  d.nA = axis == 1 ? g.i0.size : 1;
+  d.nB = (int)cols;
+  d.tw = be->twiddle(prec, N);
+  d.inStrideB = 1;
+  if (mode == AX_C2R) {   // complex side in: the caller's half spectrum [a][N/2+1][cols]
+    d.in = in;
+    d.inStrideA = axis == 1 ? (long long)(N / 2 + 1) * cols : 0;
+    d.inStrideI = cols;
+  } else {                // real side in: own A after the exchange, or the caller's block when the axis is local
+    d.in = ex ? (peerA.empty() ? nullptr : peerA[self]) : in;
+    d.inStrideA = axis == 1 ? (long long)N * cols : 0;
+    d.inStrideI = cols;
+  }
+  if (mode == AX_R2C) {   // complex side out: the caller's buffer
+    set_segs_common(d, 1, N);
+    d.seg[0].base = out;
+    d.seg[0].strideA = axis == 1 ? (long long)(N / 2 + 1) * cols : 0;
+    d.seg[0].strideB = 1;
+    d.seg[0].strideI = cols;
+  } else if (!ex) {       // real side out, local
+    set_segs_common(d, 1, N);
+    d.seg[0].base = out;
+    d.seg[0].strideA = axis == 1 ? (long long)N * cols : 0;
+    d.seg[0].strideB = 1;
+    d.seg[0].strideI = cols;
+  } else if (axis == 1) { // real side out: row peers' B in the physical layout [i0][i1][N2], entered at column n2b.start
+    const int P1 = g.np[1];
+    set_segs_common(d, P1, ceil_blk(N, P1));
+    for (int p = 0; p < P1; ++p) {
+      const Blk i1p = block_of(N, P1, p);
+      const int r = rank_of(g.np, g.coords[0], p);
+      d.seg[p].base = offs(peerB[r], g.n2b.start, rs);
+      d.seg[p].strideA = (long long)i1p.size * g.n[2];
+      d.seg[p].strideB = 1;
+      d.seg[p].strideI = g.n[2];
+    }
+  } else {                // column peers' B, physical layout [i0][M], entered at flat index mb.start
+    const int P0 = g.np[0];
+    set_segs_common(d, P0, ceil_blk(N, P0));
+    for (int q = 0; q < P0; ++q) {
+      const int r = rank_of(g.np, q, g.coords[1]);
+      d.seg[q].base = offs(peerB[r], g.mb.start, rs);
+      d.seg[q].strideA = 0;
+      d.seg[q].strideB = 1;
+      d.seg[q].strideI = g.M;
+    }
+  }
+  if (mode == AX_DERIV) {
+    d.op = OP_GRAD;
+    d.opAxis = axis;
+    d.kind[axis] = 0;
+    d.n[axis] = N;
+    d.scale = 1.0 / (double)N;
+  }
+  l.kind = mode == AX_R2C ? K_STRIDED_R2C : mode == AX_C2R ? K_STRIDED_C2R : K_STRIDED_DERIV;
+  l.prec = prec;
+  l.fftN = N;
+  l.inverse = mode == AX_C2R;
+  l.desc = d;
+  l.slot = 8;
+  return l;
+}
+
+// Z pass alone, caller's buffers on both sides: dense [i0][i1][N2] real <-> dense [i0][i1][N2c] complex
+static Launch z_local(const Plan& p, bool inverse, const void* in, void* out) {
+  Launch l = inverse ? p.inv_z(out, false) : p.fwd_z(in, false);
+  StageDesc& d = l.desc;
+  const Geometry& g = p.g;
+  if (inverse) {
+    d.in = in;
+    d.inStrideA = (long long)g.n2c * g.i1.size;
+    d.inStrideB = g.n2c;
+  } else {
+    d.nseg = 1;
+    d.blk = g.n2c;
+    d.blkMagic = blk_magic(d.blk);
+    d.seg[0].base = out;
+    d.seg[0].strideA = (long long)g.n2c * g.i1.size;
+    d.seg[0].strideB = g.n2c;
+    d.seg[0].strideI = 1;
+  }
+  l.slot = 8;
+  return l;
+}
+
+int Plan::execute_r2c_axis(int axis, const void* in, void* out) {
+  int rc;
+  if (axis == 2) {
+    Launch z = z_local(*this, false, in, out);
+    return empty(z) ? 0 : be->launch(z);
+  }
+  const bool ex = ax_exchanges(axis);
+  if (ex) {
+    Launch c = ax_copy_in(axis, in);
+    if (!empty(c) && (rc = be->launch(c))) return rc;
+    if ((rc = be->barrier())) return rc;
+  }
+  Launch s = ax_stage(axis, AX_R2C, in, out);
+  if (!empty(s) && (rc = be->launch(s))) return rc;
+  if (ex && (rc = be->barrier())) return rc;   // A was read after the exchange barrier: fence it from the next operation
+  return 0;
+}
+
+int Plan::execute_c2r_axis(int axis, const void* in, void* out) {
+  int rc;
+  if (axis == 2) {
+    Launch z = z_local(*this, true, in, out);
+    return empty(z) ? 0 : be->launch(z);
+  }
+  const bool ex = ax_exchanges(axis);
+  if (ex && (rc = be->barrier())) return rc;   // B is written first thing: wait for the peers' previous operation
+  Launch s = ax_stage(axis, AX_C2R, in, out);
+  if (!empty(s) && (rc = be->launch(s))) return rc;
+  if (ex) {
+    if ((rc = be->barrier())) return rc;
+    Launch c = ax_copy_out(out);
+    if (!empty(c) && (rc = be->launch(c))) return rc;
+  }
+  return 0;
+}
+
+int Plan::execute_deriv_axis(int axis, const void* in, void* out, bool accumulate, void* spec) {
+  int rc;
+  if (axis == 2) {
+    // r2c into the scratch spectrum, then c2r with i*k_z/N2 applied to its loads: two array passes, no exchange
+    Launch z = z_local(*this, false, in, spec);
+    if (!empty(z) && (rc = be->launch(z))) return rc;
+    Launch zi = z_local(*this, true, spec, out);
+    zi.desc.op = OP_GRAD;
+    zi.desc.opAxis = 2;
+    zi.desc.kind[2] = 0;
+    zi.desc.n[2] = g.n[2];
+    zi.desc.scale = 1.0 / (double)g.n[2];
+    zi.desc.accumulate = accumulate ? 1 : 0;
+    if (!empty(zi) && (rc = be->launch(zi))) return rc;
+    return 0;
+  }
+  const bool ex = ax_exchanges(axis);
+  if (ex) {
+    Launch c = ax_copy_in(axis, in);
+    if (!empty(c) && (rc = be->launch(c))) return rc;
+    if ((rc = be->barrier())) return rc;
+  }
+  Launch s = ax_stage(axis, AX_DERIV, in, out);
+  if (!ex) s.desc.accumulate = accumulate ? 1 : 0;
+  if (!empty(s) && (rc = be->launch(s))) return rc;
+  if (ex) {
+    if ((rc = be->barrier())) return rc;
+    Launch c = ax_copy_out(out);
+    c.desc.accumulate = accumulate ? 1 : 0;
+    if (!empty(c) && (rc = be->launch(c))) return rc;
+  }
+  return 0;
+}
+
+int Plan::execute_grad_axes(const void* in, void* const outs[3], int comps, void* spec) {
+  for (int ax = 0; ax < 3; ++ax) {
+    if (!(comps & (1 << ax))) continue;
+    if (int rc = execute_deriv_axis(ax, in, outs[ax], false, spec)) return rc;
+  }
+  return 0;
+}
+
+int Plan::execute_divergence_axes(const void* const ins[3], void* out, void* spec) {
+  for (int ax = 0; ax < 3; ++ax)
+    if (int rc = execute_deriv_axis(ax, ins[ax], out, ax > 0, spec)) return rc;
   return 0;
 }
 

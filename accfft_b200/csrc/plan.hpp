@@ -8,11 +8,15 @@
 #include <string>
 #include <vector>
 #include "decomp.hpp"
-#include "stage.cuh"
+#include "stage_real.cuh"
 
 namespace accfft_b200 {
 
-enum Kind : int { K_STRIDED_C2C = 0, K_CONTIG_C2C = 1, K_CONTIG_R2C = 2, K_CONTIG_C2R = 3, K_COPY = 4 };
+enum Kind : int {
+  K_STRIDED_C2C = 0, K_CONTIG_C2C = 1, K_CONTIG_R2C = 2, K_CONTIG_C2R = 3, K_COPY = 4,
+  // real transforms along a strided axis (stage_real.cuh): the single-axis executes and the per-axis derivative
+  K_STRIDED_R2C = 5, K_STRIDED_C2R = 6, K_STRIDED_DERIV = 7, K_COPY_REAL = 8
+};
 enum Prec : int { PREC_DOUBLE = 0, PREC_FLOAT = 1 };
 
 struct Launch {
@@ -21,7 +25,9 @@ struct Launch {
   int fftN;        // length of the complex engine transform (M = N/2 for r2c / c2r)
   bool inverse;
   bool dry;        // true: only load / configure the kernel (plan time), do not launch
-  int slot;        // profiling slot: 0 fwd Z, 1 fwd Y, 2 fwd X, 3 inv X, 4 inv Y, 5 inv Z  (6 = barrier)
+  int slot;        // profiling slot: 0 fwd Z, 1 fwd Y, 2 fwd X, 3 inv X, 4 inv Y, 5 inv Z  (6 = barrier),
+                   // 7 = real copy / exchange stages, 8 = single-axis real transform / derivative stages
+  long long copyN; // K_COPY_REAL: extent of the fastest input index k (a flat plane index on the x path)
   int variant;     // strided stages: 0 = backend's choice (plan-time tuning / heuristic), 1 = plain kernel, 2 = TMA-pipelined kernel
   StageDesc desc;
 };
@@ -44,6 +50,10 @@ struct Geometry {
   Blk i0, i1;              // input block:  [i0.size][i1.size][N2]
   Blk k2;                  // after exchange 1: [i0.size][N1][k2.size]
   Blk k1;                  // after exchange 2: [N0][k1.size][k2.size]  (= output)
+  // single-axis REAL paths of r2c plans (src/accfft_common.cpp:150-190: osize_y / osize_x)
+  Blk n2b;                 // y path: real [i0.size][N1][n2b.size], N2 split over the row group
+  long long M;             // x path: the local (i1, N2) plane flattened, M = i1.size * N2 ...
+  Blk mb;                  // ... and split over the column group: real [N0][mb.size]
   LocalSizes L;
 };
 
@@ -80,6 +90,22 @@ struct Plan {
   Launch inv_x(const void* in) const;
   Launch inv_y() const;
   Launch inv_z(void* out, bool out_padded) const;
+
+  // ---- single-axis real transforms and the per-axis derivative (r2c plans; axis 0 = x, 1 = y, 2 = z) -------------
+  // mode of ax_stage
+  enum AxMode : int { AX_R2C = 0, AX_C2R = 1, AX_DERIV = 2 };
+  bool ax_exchanges(int axis) const { return axis == 1 ? g.np[1] > 1 : axis == 0 ? g.np[0] > 1 : false; }
+  Launch ax_copy_in(int axis, const void* in) const;                 // user real block -> peers' A in the axis layout
+  Launch ax_stage(int axis, int mode, const void* in, void* out) const;   // x / y axes (strided kernels)
+  Launch ax_copy_out(void* out) const;                               // own B (physical layout) -> user real block
+  // reference: accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t (src/accfft_gpu.cpp:1212-1604); layouts osize_y/yi, osize_x/xi
+  int execute_r2c_axis(int axis, const void* in, void* out);
+  int execute_c2r_axis(int axis, const void* in, void* out);
+  // d/dx_axis of a real field, spectral, normalised; accumulate: out += (divergence)
+  int execute_deriv_axis(int axis, const void* in, void* out, bool accumulate, void* spec);
+  // per-axis schemes of the operators (src/operators_gpu.txx:172-278, :336-553)
+  int execute_grad_axes(const void* in, void* const outs[3], int comps, void* spec);
+  int execute_divergence_axes(const void* const ins[3], void* out, void* spec);
 
   bool check_supported();
   // Load and configure every kernel the plan can launch (CUDA loads kernels lazily, and a first-use load may

@@ -448,7 +448,14 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
   if (valid) {
     const SegDst& sd = d.seg[0];
     cplx<T>* out = (cplx<T>*)((T*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB);
-    pass_foreach<S, S::NP - 1>(v, t, [&](int nidx, cplx<T>& r) { out[nidx] = cswap(r); });
+    if (d.accumulate) {   // divergence: this component is added to what the earlier ones left in the output
+      pass_foreach<S, S::NP - 1>(v, t, [&](int nidx, cplx<T>& r) {
+        const cplx<T> o = out[nidx];
+        out[nidx] = {o.x + r.y, o.y + r.x};
+      });
+    } else {
+      pass_foreach<S, S::NP - 1>(v, t, [&](int nidx, cplx<T>& r) { out[nidx] = cswap(r); });
+    }
   }
 }
 

@@ -173,12 +173,20 @@ ACC_HD void strided_deriv_body(const StageDesc& d, Ctx& ctx) {
   cplx<T>* sm = (cplx<T>*)ctx.smem();
   auto addr = [&](int i) { return sm + S::phys(i) * TC + c; };
   fft_passes<S>(v, t, w1, addr, [&]() { ctx.sync(); });
-  // symbol multiply in output order, then back to pass-0 gather order through the tile (swapped for the inverse)
-  if constexpr (S::NP > 1) ctx.sync();
-  pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(apply_op(d, r, k, a, b0)); });
-  ctx.sync();
-  pass_gather<S, 0>(v, t, addr);
-  if constexpr (S::NP > 1) ctx.sync();
+  // symbol multiply in output order (index j + r*N/R_last).  When the first and the last radix agree that IS the pass-0
+  // gather order of the inverse (index j + r*N/R_0), so the registers go straight into the second set of passes;
+  // otherwise they are re-ordered through the tile.  (swapped: inverse = swap . forward . swap)
+  constexpr bool kSameOrder = S::radix(0) == S::radix(S::NP - 1);
+  if constexpr (kSameOrder) {
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(apply_op(d, r, k, a, b0)); });
+    if constexpr (S::NP > 1) ctx.sync();   // the forward's last gathers are done before the inverse scatters again
+  } else {
+    if constexpr (S::NP > 1) ctx.sync();
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(apply_op(d, r, k, a, b0)); });
+    ctx.sync();
+    pass_gather<S, 0>(v, t, addr);
+    if constexpr (S::NP > 1) ctx.sync();
+  }
   fft_passes<S>(v, t, w1, addr, [&]() { ctx.sync(); });
   if (valid0)
     pass_foreach<S, S::NP - 1>(v, t, [&](int n, cplx<T>& r) { store_real_pair(d, cswap(r), n, a, b0, valid1); });

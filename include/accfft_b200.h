@@ -109,9 +109,10 @@ int accfftb_plan_set_blocking(accfftb_plan* plan, int blocking);
 /* Per-launch device timing: while on, every stage / barrier kernel is bracketed by a CUDA event pair on
  * the plan's stream (no host synchronisation).  _profile_read synchronises the stream, returns the summed
  * milliseconds and launch counts per slot since the last read, and resets.  Slots: 0 forward Z pass,
- * 1 forward Y, 2 forward X, 3 inverse X, 4 inverse Y, 5 inverse Z, 6 inter-GPU barrier.  (The reference
- * only offers the coarse timer[5] of doc/timing.md.) */
-#define ACCFFTB_PROFILE_SLOTS 7
+ * 1 forward Y, 2 forward X, 3 inverse X, 4 inverse Y, 5 inverse Z, 6 inter-GPU barrier, 7 real copy / exchange
+ * stages of the single-axis paths, 8 single-axis transform / derivative stages.  (The reference only offers the
+ * coarse timer[5] of doc/timing.md.) */
+#define ACCFFTB_PROFILE_SLOTS 9
 int accfftb_plan_set_profiling(accfftb_plan* plan, int on);
 int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOTS], long long count[ACCFFTB_PROFILE_SLOTS]);
 
@@ -150,6 +151,17 @@ int accfftb_execute_c2r(accfftb_plan* plan, const void* data, void* data_out, do
 /* accfft_execute_c2c_gpu / _gpuf (:943-1136): direction = ACCFFTB_FORWARD / ACCFFTB_BACKWARD. */
 int accfftb_execute_c2c(accfftb_plan* plan, int direction, const void* data, void* data_out, double* timer, int xyz);
 
+/* ---- single-axis real transforms: accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t (src/accfft_gpu.cpp:1212-1604), the
+ * building blocks of the reference's per-axis gradient.  r2c plans only.  axis: 0 = x, 1 = y, 2 = z.
+ * Real side: the [isize] block.  Complex side (sizes / starts: accfftb_stage_size which = 0 for z, 4 for y, 6 for x):
+ *   z: [isize0][isize1][N2/2+1]                                                     (osize_0)
+ *   y: [isize0][N1/2+1][n2b],  n2b = this rank's block of N2 over the row group     (osize_yi; starts: ostart_y)
+ *   x: [N0/2+1][mb],  mb = this rank's block of the flattened local plane isize1*N2 over the column group (osize_xi)
+ * Unnormalised, like the reference (c2r(r2c(x)) = N_axis * x).  Neither call overwrites its input (the reference's
+ * c2r_x transforms in place in `data`, :1535-1538). */
+int accfftb_execute_r2c_axis(accfftb_plan* plan, int axis, const void* data, void* data_out, double* timer);
+int accfftb_execute_c2r_axis(accfftb_plan* plan, int axis, const void* data, void* data_out, double* timer);
+
 /* ---- spectral operators (accfft_operators_gpu.h:44-67; src/operators_gpu.txx; kernels
  * src/operators_cuda.cu:15-215).  Real [isize] in, real [isize] out, normalised, Nyquist modes zeroed.
  * The symbol multiply and the 1/N scale are fused into the X-pass stores (no Hadamard kernels, no
@@ -161,6 +173,13 @@ int accfftb_biharmonic(accfftb_plan* plan, const void* A, void* BA, double* time
  * (src/operators_gpu.txx:172-278); unselected outputs may be NULL. */
 int accfftb_grad(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int xyz, double* timer);
 int accfftb_divergence(accfftb_plan* plan, const void* Ax, const void* Ay, const void* Az, void* div, double* timer);
+/* accfftb_grad / accfftb_divergence follow the reference's default per-axis scheme (accfft_grad_gpu_t,
+ * src/operators_gpu.txx:172-278: a 1-D real transform along the component's axis only), with forward transform,
+ * i*k multiply and inverse transform fused into ONE kernel per component for x and y (one read + one write of the
+ * field) and two passes for z.  The _slow variants are the reference's accfft_grad_gpu_slow_t /
+ * accfft_divergence_gpu_slow_t (:72-170, :448-553): full 3-D transforms (1 forward + 1 inverse per component). */
+int accfftb_grad_slow(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int xyz, double* timer);
+int accfftb_divergence_slow(accfftb_plan* plan, const void* Ax, const void* Ay, const void* Az, void* div, double* timer);
 
 #ifdef __cplusplus
 }

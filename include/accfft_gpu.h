@@ -83,4 +83,20 @@ template <typename Tc, typename T>
 void accfft_execute_c2r_gpu_t(accfft_plan_gpu* plan, Tc* data, T* data_out, double* timer = NULL,
                               std::bitset<3> XYZ = 111);
 
+// single-axis real transforms (reference: include/accfft_gpu.h:137-156; src/accfft_gpu.cpp:1212-1604).  Complex side layouts:
+// z [isize0][isize1][N2/2+1] (osize_0), y [isize0][N1/2+1][N2 block of the row group] (osize_yi),
+// x [N0/2+1][block of the flattened isize1*N2 plane over the column group] (osize_xi).
+template <typename T, typename Tc>
+void accfft_execute_r2c_z_gpu_t(accfft_plan_gpu* plan, T* data, Tc* data_out, double* timer = NULL);
+template <typename Tc, typename T>
+void accfft_execute_c2r_z_gpu_t(accfft_plan_gpu* plan, Tc* data, T* data_out, double* timer = NULL);
+template <typename T, typename Tc>
+void accfft_execute_r2c_y_gpu_t(accfft_plan_gpu* plan, T* data, Tc* data_out, double* timer = NULL);
+template <typename Tc, typename T>
+void accfft_execute_c2r_y_gpu_t(accfft_plan_gpu* plan, Tc* data, T* data_out, double* timer = NULL);
+template <typename T, typename Tc>
+void accfft_execute_r2c_x_gpu_t(accfft_plan_gpu* plan, T* data, Tc* data_out, double* timer = NULL);
+template <typename Tc, typename T>
+void accfft_execute_c2r_x_gpu_t(accfft_plan_gpu* plan, Tc* data, T* data_out, double* timer = NULL);
+
 #endif

@@ -241,6 +241,38 @@ def assemble_input(blocks: List[np.ndarray], n, np_) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# single-axis real transforms: accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t (src/accfft_gpu.cpp:1212-1604)
+# --------------------------------------------------------------------------------------
+def axis_forward(x: np.ndarray, axis: int) -> np.ndarray:
+    """Global result of the single-axis r2c: unnormalised real DFT along `axis` only (0 = x, 1 = y, 2 = z),
+    keeping k in [0, N_axis/2] (cufftExecD2Z of fplan_x / fplan_y / fplan_0, src/accfft_gpu.cpp:1234, :1370, :1524)."""
+    return np.fft.rfft(np.asarray(x, np.float64), axis=axis)
+
+
+def axis_inverse(X: np.ndarray, n, axis: int) -> np.ndarray:
+    """Global result of the single-axis c2r: unnormalised (c2r(r2c(x)) = N_axis * x)."""
+    return np.fft.irfft(X, n=n[axis], axis=axis) * n[axis]
+
+
+def axis_local_spectrum(Xa: np.ndarray, n, np_, coords, axis: int) -> np.ndarray:
+    """Rank (c0,c1)'s block of the single-axis spectrum Xa = axis_forward(x, axis), in the reference's layouts:
+      z: [isize0][isize1][N2/2+1]                       (osize_0,  src/accfft_common.cpp:110-112)
+      y: [isize0][N1/2+1][block of N2 over P1]          (osize_yi, :150-162: N2 is split over the row group)
+      x: [N0/2+1][block of the flattened local plane isize1*N2 over P0]   (osize_xi, :164-188)"""
+    s0, st0 = block(n[0], np_[0], coords[0])
+    s1, st1 = block(n[1], np_[1], coords[1])
+    if axis == 2:
+        return np.ascontiguousarray(Xa[st0:st0 + s0, st1:st1 + s1, :])
+    if axis == 1:
+        s2, st2 = block(n[2], np_[1], coords[1])
+        return np.ascontiguousarray(Xa[st0:st0 + s0, :, st2:st2 + s2])
+    M = s1 * n[2]
+    sm, stm = block(M, np_[0], coords[0])
+    plane = Xa[:, st1:st1 + s1, :].reshape(Xa.shape[0], M)
+    return np.ascontiguousarray(plane[:, stm:stm + sm])
+
+
+# --------------------------------------------------------------------------------------
 # staged (distributed) algorithm with the reference's own pack / unpack index formulas
 # --------------------------------------------------------------------------------------
 

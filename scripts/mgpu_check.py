@@ -50,11 +50,33 @@ def check(n, dims, r2c, single=False):
         errs.append(orc.rel_l2(la.cpu().numpy().reshape(loc.shape), orc.local_input(orc.laplace(x), n, dims, comm.coords)))
         g = [torch.zeros_like(xd) for _ in range(3)]
         p.grad(g[0], g[1], g[2], xd)
+        gs = [torch.zeros_like(xd) for _ in range(3)]
+        p.grad_slow(gs[0], gs[1], gs[2], xd)
+        dv, dvs = torch.zeros_like(xd), torch.zeros_like(xd)
+        p.divergence(dv, g[0], g[1], g[2])
+        p.divergence_slow(dvs, g[0], g[1], g[2])
+        gx = [orc.grad(x, ax) for ax in range(3)]
+        want_div = orc.local_input(orc.divergence(*gx), n, dims, comm.coords)
         for ax in range(3):
-            errs.append(orc.rel_l2(g[ax].cpu().numpy().reshape(loc.shape), orc.local_input(orc.grad(x, ax), n, dims, comm.coords)))
-    elif r2c:
+            errs.append(orc.rel_l2(g[ax].cpu().numpy().reshape(loc.shape), orc.local_input(gx[ax], n, dims, comm.coords)))
+            errs.append(orc.rel_l2(gs[ax].cpu().numpy().reshape(loc.shape), orc.local_input(gx[ax], n, dims, comm.coords)))
+        errs.append(orc.rel_l2(dv.cpu().numpy().reshape(loc.shape), want_div))
+        errs.append(orc.rel_l2(dvs.cpu().numpy().reshape(loc.shape), want_div))
+    elif r2c:   # empty rank: still takes part in every collective call
         la = torch.zeros_like(xd); p.laplace(la, xd)
-        g = [torch.zeros_like(xd) for _ in range(3)]; p.grad(g[0], g[1], g[2], xd)
+        g = [torch.zeros_like(xd) for _ in range(3)]; p.grad(g[0], g[1], g[2], xd); p.grad_slow(g[0], g[1], g[2], xd)
+        p.divergence(la, g[0], g[1], g[2]); p.divergence_slow(la, g[0], g[1], g[2])
+    if r2c:
+        # single-axis real transforms (accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t): per-rank half spectra + round trip
+        for axis in (0, 1, 2):
+            p.execute_r2c_axis(axis, xd, out)
+            ref = orc.axis_local_spectrum(orc.axis_forward(x, axis), n, dims, comm.coords, axis)
+            b2 = torch.zeros_like(xd)
+            p.execute_c2r_axis(axis, out, b2)
+            if ref.size:
+                errs.append(orc.rel_l2(out.cpu().numpy().view(cdt)[:ref.size].reshape(ref.shape), ref))
+            if loc.size:
+                errs.append(orc.rel_l2(b2.cpu().numpy().reshape(loc.shape) / n[axis], loc))
     e = max(errs) if errs else 0.0
     t = torch.tensor([e], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -110,8 +132,12 @@ def bench(n, dims, r2c=True, iters=20, single=False):
         # operator timings (report as time, not GFLOP/s)
         la = torch.zeros_like(x)
         g = [torch.zeros_like(x) for _ in range(3)]
-        for name, fn in (("laplace", lambda: p.laplace(la, x)), ("grad", lambda: p.grad(g[0], g[1], g[2], x)),
-                         ("divergence", lambda: p.divergence(la, g[0], g[1], g[2]))):
+        for name, fn in (("laplace", lambda: p.laplace(la, x)), ("grad (per-axis)", lambda: p.grad(g[0], g[1], g[2], x)),
+                         ("grad_slow (3-D)", lambda: p.grad_slow(g[0], g[1], g[2], x)),
+                         ("grad x", lambda: p.grad(g[0], None, None, x, xyz=1)), ("grad y", lambda: p.grad(None, g[1], None, x, xyz=2)),
+                         ("grad z", lambda: p.grad(None, None, g[2], x, xyz=4)),
+                         ("divergence (per-axis)", lambda: p.divergence(la, g[0], g[1], g[2])),
+                         ("divergence_slow (3-D)", lambda: p.divergence_slow(la, g[0], g[1], g[2]))):
             with torch.cuda.stream(st):
                 fn()
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()

@@ -145,6 +145,17 @@ static void emu_launch_sched(const Launch& l) {
       run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2r_body<T, S, C::PC>(d, c); });
       break;
     }
+    case K_STRIDED_R2C:
+    case K_STRIDED_C2R:
+    case K_STRIDED_DERIV: {
+      const long long nb = (long long)d.nA * ((d.nB + 2 * C::TC - 1) / (2 * C::TC));
+      run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) {
+        if (l.kind == K_STRIDED_R2C) strided_r2c_body<T, S, C::TC>(d, c);
+        else if (l.kind == K_STRIDED_C2R) strided_c2r_body<T, S, C::TC>(d, c);
+        else strided_deriv_body<T, S, C::TC>(d, c);
+      });
+      break;
+    }
     default:
       fprintf(stderr, "emul: unsupported kind %d\n", (int)l.kind);
       abort();
@@ -171,6 +182,14 @@ static void emu_copy_stage(const Launch& l) {
 }
 
 static void emu_launch(const Launch& l) {
+  if (l.kind == K_COPY_REAL) {   // same element walk as k_copy_real in engine.cu
+    const long long total = (long long)l.desc.nA * l.desc.nB * l.copyN;
+    for (long long idx = 0; idx < total; ++idx) {
+      if (l.prec == PREC_DOUBLE) copy_real_element<double>(l.desc, idx, l.copyN);
+      else copy_real_element<float>(l.desc, idx, l.copyN);
+    }
+    return;
+  }
   if (l.kind == K_COPY) {
     if (l.prec == PREC_DOUBLE) emu_copy_stage<double>(l);
     else emu_copy_stage<float>(l);
@@ -359,6 +378,55 @@ int emu_execute_div(void* h, void** ix, void** iy, void** iz, void** out) {
     th.emplace_back([&, r]() {
       const void* ins[3] = {ix[r], iy[r], iz[r]};
       rc[r] = w->plans[r].execute_divergence(ins, out[r], w->spec[r].data());
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w->nprocs; ++r)
+    if (rc[r]) return rc[r];
+  return canaries_ok(w) ? 0 : -99;
+}
+
+// single-axis real paths: mode 0 = r2c, 1 = c2r, 2 = derivative, 3 = derivative accumulated into out
+int emu_execute_axis(void* h, int mode, int axis, void** in, void** out) {
+  EmuWorld* w = (EmuWorld*)h;
+  std::vector<std::thread> th;
+  std::vector<int> rc(w->nprocs, 0);
+  for (int r = 0; r < w->nprocs; ++r)
+    th.emplace_back([&, r]() {
+      Plan& p = w->plans[r];
+      if (mode == 0) rc[r] = p.execute_r2c_axis(axis, in[r], out[r]);
+      else if (mode == 1) rc[r] = p.execute_c2r_axis(axis, in[r], out[r]);
+      else rc[r] = p.execute_deriv_axis(axis, in[r], out[r], mode == 3, w->spec[r].data());
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w->nprocs; ++r)
+    if (rc[r]) return rc[r];
+  return canaries_ok(w) ? 0 : -99;
+}
+
+// per-axis operator schemes (execute_grad_axes / execute_divergence_axes)
+int emu_execute_grad_axes(void* h, void** in, void** ox, void** oy, void** oz, int comps) {
+  EmuWorld* w = (EmuWorld*)h;
+  std::vector<std::thread> th;
+  std::vector<int> rc(w->nprocs, 0);
+  for (int r = 0; r < w->nprocs; ++r)
+    th.emplace_back([&, r]() {
+      void* outs[3] = {ox[r], oy[r], oz[r]};
+      rc[r] = w->plans[r].execute_grad_axes(in[r], outs, comps, w->spec[r].data());
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w->nprocs; ++r)
+    if (rc[r]) return rc[r];
+  return canaries_ok(w) ? 0 : -99;
+}
+
+int emu_execute_div_axes(void* h, void** ix, void** iy, void** iz, void** out) {
+  EmuWorld* w = (EmuWorld*)h;
+  std::vector<std::thread> th;
+  std::vector<int> rc(w->nprocs, 0);
+  for (int r = 0; r < w->nprocs; ++r)
+    th.emplace_back([&, r]() {
+      const void* ins[3] = {ix[r], iy[r], iz[r]};
+      rc[r] = w->plans[r].execute_divergence_axes(ins, out[r], w->spec[r].data());
     });
   for (auto& t : th) t.join();
   for (int r = 0; r < w->nprocs; ++r)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "_build", "libemul.so")
 SOURCES = [os.path.join(HERE, "emul.cpp"), os.path.join(ROOT, "accfft_b200", "csrc", "plan.cpp")]
 HEADERS = [os.path.join(ROOT, "accfft_b200", "csrc", f)
-           for f in ("fft_engine.cuh", "stage.cuh", "plan.hpp", "decomp.hpp", "kernel_cfg.hpp", "schedules.def")]
+           for f in ("fft_engine.cuh", "stage.cuh", "stage_real.cuh", "plan.hpp", "decomp.hpp", "kernel_cfg.hpp", "schedules.def")]
 
 sys.path.insert(0, ROOT)
 from oracle import accfft_oracle as orc  # noqa: E402
@@ -56,6 +56,12 @@ def lib():
         _lib.emu_execute_grad.argtypes = [ctypes.c_void_p, pp, pp, pp, pp, ctypes.c_int]
         _lib.emu_execute_div.restype = ctypes.c_int
         _lib.emu_execute_div.argtypes = [ctypes.c_void_p, pp, pp, pp, pp]
+        _lib.emu_execute_axis.restype = ctypes.c_int
+        _lib.emu_execute_axis.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, pp, pp]
+        _lib.emu_execute_grad_axes.restype = ctypes.c_int
+        _lib.emu_execute_grad_axes.argtypes = [ctypes.c_void_p, pp, pp, pp, pp, ctypes.c_int]
+        _lib.emu_execute_div_axes.restype = ctypes.c_int
+        _lib.emu_execute_div_axes.argtypes = [ctypes.c_void_p, pp, pp, pp, pp]
     return _lib
 
 
@@ -180,19 +186,62 @@ def _blocks_real(w, outs):
     return blocks
 
 
-def grad(w, x_global, comps=7):
+def axis_r2c(w, x_global, axis):
+    """single-axis forward: per-rank half spectra in the reference's osize_0 / osize_yi / osize_xi layouts"""
+    ins = _local_real(w, x_global)
+    outs = w.alloc_out()
+    rc = lib().emu_execute_axis(w.h, 0, axis, _ptrs(ins), _ptrs(outs))
+    if rc:
+        raise RuntimeError(f"emu_execute_axis rc={rc}")
+    Xa = orc.axis_forward(x_global, axis)
+    res = []
+    for r in range(w.nprocs):
+        ref = orc.axis_local_spectrum(Xa, w.n, w.np_, w.coords(r), axis)
+        res.append((outs[r].view(w.cdt)[:ref.size].reshape(ref.shape).copy(), ref))
+    return res
+
+
+def axis_c2r(w, x_global, axis):
+    """single-axis inverse of the oracle's local spectra -> real blocks"""
+    Xa = orc.axis_forward(x_global, axis)
+    ins = []
+    for r in range(w.nprocs):
+        loc = orc.axis_local_spectrum(Xa, w.n, w.np_, w.coords(r), axis).astype(w.cdt)
+        ins.append(np.ascontiguousarray(loc) if loc.size else np.zeros(2, dtype=w.cdt))
+    outs = w.alloc_out()
+    rc = lib().emu_execute_axis(w.h, 1, axis, _ptrs(ins), _ptrs(outs))
+    if rc:
+        raise RuntimeError(f"emu_execute_axis rc={rc}")
+    return _blocks_real(w, outs)
+
+
+def axis_deriv(w, x_global, axis, accumulate_onto=None):
+    ins = _local_real(w, x_global)
+    outs = w.alloc_out()
+    if accumulate_onto is not None:
+        for r, b in enumerate(_local_real(w, accumulate_onto)):
+            outs[r][:b.size] = b.ravel()
+    rc = lib().emu_execute_axis(w.h, 3 if accumulate_onto is not None else 2, axis, _ptrs(ins), _ptrs(outs))
+    if rc:
+        raise RuntimeError(f"emu_execute_axis rc={rc}")
+    return _blocks_real(w, outs)
+
+
+def grad(w, x_global, comps=7, fast=False):
     ins = _local_real(w, x_global)
     outs = [w.alloc_out() for _ in range(3)]
-    rc = lib().emu_execute_grad(w.h, _ptrs(ins), _ptrs(outs[0]), _ptrs(outs[1]), _ptrs(outs[2]), comps)
+    fn = lib().emu_execute_grad_axes if fast else lib().emu_execute_grad
+    rc = fn(w.h, _ptrs(ins), _ptrs(outs[0]), _ptrs(outs[1]), _ptrs(outs[2]), comps)
     if rc:
         raise RuntimeError(f"emu_execute_grad rc={rc}")
     return [_blocks_real(w, o) for o in outs]
 
 
-def divergence(w, ax, ay, az):
+def divergence(w, ax, ay, az, fast=False):
     ins = [_local_real(w, v) for v in (ax, ay, az)]
     out = w.alloc_out()
-    rc = lib().emu_execute_div(w.h, _ptrs(ins[0]), _ptrs(ins[1]), _ptrs(ins[2]), _ptrs(out))
+    fn = lib().emu_execute_div_axes if fast else lib().emu_execute_div
+    rc = fn(w.h, _ptrs(ins[0]), _ptrs(ins[1]), _ptrs(ins[2]), _ptrs(out))
     if rc:
         raise RuntimeError(f"emu_execute_div rc={rc}")
     return _blocks_real(w, out)

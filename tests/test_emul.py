@@ -93,6 +93,53 @@ def test_single_precision(n, np_):
     w.close()
 
 
+AXIS_CASES = [((8, 8, 8), (1, 1)), ((6, 10, 8), (1, 1)), ((8, 8, 8), (1, 2)), ((8, 8, 8), (2, 1)), ((12, 10, 16), (2, 4)),
+              ((6, 12, 10), (3, 2)), ((5, 6, 6), (4, 2)), ((3, 5, 4), (4, 4)), ((9, 15, 10), (2, 2)), ((32, 24, 20), (2, 2))]
+
+
+@pytest.mark.parametrize("single", [False, True])
+@pytest.mark.parametrize("n,np_", AXIS_CASES)
+def test_single_axis_real_transforms(n, np_, single):
+    """accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t (src/accfft_gpu.cpp:1212-1604): per-rank half spectra in the reference's
+    osize_xi / osize_yi / osize_0 layouts, round trip = N_axis * x, and the fused per-axis derivative (with and
+    without accumulation) -- odd lengths, odd column counts (scalar fallback of the pair accesses), empty ranks."""
+    tol = 1e-5 if single else 1e-12
+    x = orc.synthetic_real(n, 11)
+    y = orc.synthetic_real(n, 12)
+    w = emu.World(n, np_, r2c=True, single=single)
+    for axis in (0, 1, 2):
+        res = emu.axis_r2c(w, x, axis)
+        num = sum(float(np.sum(np.abs(a - b) ** 2)) for a, b in res)
+        den = sum(float(np.sum(np.abs(b) ** 2)) for a, b in res)
+        assert np.sqrt(num / den) < tol, axis
+        assert all(a.shape == b.shape for a, b in res)
+        assert orc.rel_l2(orc.assemble_input(emu.axis_c2r(w, x, axis), n, np_), x * n[axis]) < tol, axis
+        assert orc.rel_l2(orc.assemble_input(emu.axis_deriv(w, x, axis), n, np_), orc.grad(x, axis)) < tol, axis
+        acc = orc.assemble_input(emu.axis_deriv(w, x, axis, accumulate_onto=y), n, np_)
+        assert orc.rel_l2(acc, orc.grad(x, axis) + y) < tol, axis
+    w.close()
+
+
+@pytest.mark.parametrize("n,np_", [((8, 8, 8), (1, 1)), ((12, 10, 16), (2, 2)), ((5, 6, 6), (2, 1)), ((9, 5, 10), (1, 2)),
+                                   ((6, 12, 10), (3, 2)), ((12, 10, 16), (2, 4))])
+def test_grad_divergence_per_axis_scheme(n, np_):
+    """accfft_grad_gpu_t / accfft_divergence_gpu_t (src/operators_gpu.txx:172-278, :448-553): same numbers as the
+    full-3-D ("slow") scheme and the oracle."""
+    x = orc.synthetic_real(n, 17)
+    w = emu.World(n, np_, r2c=True)
+    g = emu.grad(w, x, fast=True)
+    for ax in range(3):
+        assert orc.rel_l2(orc.assemble_input(g[ax], n, np_), orc.grad(x, ax)) < 1e-12, ax
+    gy = emu.grad(w, x, comps=0b010, fast=True)
+    assert orc.rel_l2(orc.assemble_input(gy[1], n, np_), orc.grad(x, 1)) < 1e-12
+    a = [orc.synthetic_real(n, 20 + i) for i in range(3)]
+    dv = emu.divergence(w, *a, fast=True)
+    assert orc.rel_l2(orc.assemble_input(dv, n, np_), orc.divergence(*a)) < 1e-12
+    # the 3-D path still works afterwards on the same buffers (exchange-buffer discipline)
+    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), orc.forward_r2c(x)) < 1e-12
+    w.close()
+
+
 def test_unsupported_length_is_refused():
     with pytest.raises(RuntimeError):
         emu.World((7, 8, 8), (1, 1), r2c=True)

@@ -246,6 +246,74 @@ def test_operators_against_oracle(cuda_device, n, single):
     p.destroy()
 
 
+@pytest.mark.parametrize("n,single", [((16, 20, 24), False), ((64, 64, 64), False), ((48, 40, 36), False), ((9, 15, 10), False),
+                                      ((30, 6, 50), False), ((64, 64, 64), True), ((128, 96, 160), False), ((20, 18, 12), True)])
+def test_single_axis_transforms_and_slow_operators(cuda_device, n, single):
+    """accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t (src/accfft_gpu.cpp:1212-1604) against numpy's rfft along one axis, and the
+    reference's two operator schemes (per-axis = default, full 3-D = *_slow) against the oracle and each other."""
+    torch = torch_mod()
+    rdt, cdt = dtypes(single)
+    es = 4 if single else 8
+    tol = 1e-12 if not single else 2e-5
+    x = orc.synthetic_real(n, 91)
+    p = make_plan(n, True, single)
+    xd = to_dev(x.astype(rdt), cuda_device)
+    for axis in (0, 1, 2):
+        Xa = orc.axis_forward(x, axis)
+        size, _ = p.axis_size(axis)
+        if axis == 0:
+            assert size[0] == n[0] // 2 + 1 and size[1] == n[1] * n[2]
+        out = torch.zeros(p.alloc_max // es, dtype=xd.dtype, device=cuda_device)
+        p.execute_r2c_axis(axis, xd, out)
+        got = out.cpu().numpy().view(cdt)[:Xa.size].reshape(Xa.shape)
+        assert orc.rel_l2(got, Xa) <= tol, axis
+        back = torch.zeros_like(xd)
+        p.execute_c2r_axis("xyz"[axis], out, back)
+        assert orc.rel_l2(back.cpu().numpy() / n[axis], x) <= tol, axis
+        # spectrum untouched by the inverse (the reference's c2r_x transforms its input in place)
+        assert np.array_equal(out.cpu().numpy().view(cdt)[:Xa.size].reshape(Xa.shape), got)
+    g = [torch.zeros_like(xd) for _ in range(3)]
+    gs = [torch.zeros_like(xd) for _ in range(3)]
+    p.grad(g[0], g[1], g[2], xd)
+    p.grad_slow(gs[0], gs[1], gs[2], xd)
+    for ax in range(3):
+        assert orc.rel_l2(g[ax].cpu().numpy(), orc.grad(x, ax)) <= tol
+        assert orc.rel_l2(gs[ax].cpu().numpy(), orc.grad(x, ax)) <= tol
+    a = [orc.synthetic_real(n, 95 + i) for i in range(3)]
+    ad = [to_dev(v.astype(rdt), cuda_device) for v in a]
+    dv, dvs = torch.full_like(xd, 7.0), torch.full_like(xd, 7.0)
+    p.divergence(dv, ad[0], ad[1], ad[2])
+    p.divergence_slow(dvs, ad[0], ad[1], ad[2])
+    assert orc.rel_l2(dv.cpu().numpy(), orc.divergence(*a)) <= tol
+    assert orc.rel_l2(dvs.cpu().numpy(), orc.divergence(*a)) <= tol
+    with pytest.raises(acc.AccfftError):
+        p.divergence(ad[1], ad[0], ad[1], ad[2])     # output aliasing a later input component
+    with pytest.raises(acc.AccfftError):
+        p.execute_r2c_axis(3, xd, dv)
+    p.destroy()
+
+
+def test_full_size_per_axis_gradient_512(cuda_device):
+    """BASELINE size: the fused per-axis derivative kernels against torch.fft (test-only cross-check on the device)."""
+    torch = torch_mod()
+    n = (512, 512, 512)
+    gen = torch.Generator(device=cuda_device).manual_seed(5)
+    xd = torch.rand(n, dtype=torch.float64, device=cuda_device, generator=gen) * 2 - 1
+    p = make_plan(n, True, False)
+    g = [torch.zeros_like(xd) for _ in range(3)]
+    p.grad(g[0], g[1], g[2], xd)
+    for ax in range(3):
+        k = torch.fft.fftfreq(n[ax], d=1.0 / n[ax], device=cuda_device, dtype=torch.float64)
+        k[n[ax] // 2] = 0
+        shape = [1, 1, 1]
+        shape[ax] = n[ax]
+        ref = torch.fft.ifft(torch.fft.fft(xd, dim=ax) * (1j * k.reshape(shape)), dim=ax).real
+        err = float(torch.linalg.vector_norm(g[ax] - ref) / torch.linalg.vector_norm(ref))
+        assert err <= 1e-12, (ax, err)
+        del ref
+    p.destroy()
+
+
 def test_step5_operators_closed_form_256(cuda_device):
     # steps/step5/step5_gpu.cpp: 256^3, f = sin x sin y sin z + exp(-32 |x-pi|^2); relative L1 < 1e-10 (:599)
     torch = torch_mod()
@@ -486,6 +554,62 @@ def test_multirank_threads_on_one_gpu(cuda_device, n, dims, r2c, single, stage_k
         p._h = None
 
 
+@pytest.mark.parametrize("n,dims,single", [((16, 12, 20), (2, 2), False), ((12, 10, 16), (2, 4), False), ((5, 6, 6), (4, 2), False),
+                                           ((64, 48, 40), (1, 2), False), ((64, 48, 40), (2, 1), False),
+                                           ((16, 64, 64), (2, 4), True), ((128, 96, 160), (2, 4), False)])
+def test_multirank_single_axis_threads(cuda_device, n, dims, single):
+    """single-axis real paths with their real-data exchanges (T_plan_y / T_plan_x of the reference,
+    src/accfft_gpu.cpp:369-373, :426-438) on one device, every rank a host thread"""
+    torch = torch_mod()
+    nprocs = dims[0] * dims[1]
+    rdt, cdt = dtypes(single)
+    tdt = torch.float32 if single else torch.float64
+    es = 4 if single else 8
+    tol = TOL[single]
+    x = orc.synthetic_real(n, 51)
+    comms = [acc.Comm(r, nprocs, dims) for r in range(nprocs)]
+    plans = [acc.Plan(n, comms[r], r2c=True, single=single, wire=False) for r in range(nprocs)]
+    acc.attach_local_peers(plans)
+    streams = [torch.cuda.Stream() for _ in range(nprocs)]
+    ins, spec, backs = [], [], []
+    for r in range(nprocs):
+        loc = orc.local_input(x, n, dims, comms[r].coords).astype(rdt)
+        ins.append(to_dev(loc, cuda_device) if loc.size else torch.zeros(2, dtype=tdt, device=cuda_device))
+        spec.append([torch.zeros(max(plans[r].alloc_max // es, 2), dtype=tdt, device=cuda_device) for _ in range(3)])
+        backs.append([torch.zeros_like(ins[-1]) for _ in range(3)])
+        plans[r].set_stream(streams[r].cuda_stream)
+    torch.cuda.synchronize()
+
+    def body(r):
+        with torch.cuda.stream(streams[r]):
+            for _ in range(2):   # repeated: exchange-buffer reuse across operations
+                for axis in (0, 1, 2):
+                    plans[r].execute_r2c_axis(axis, ins[r], spec[r][axis])
+                    plans[r].execute_c2r_axis(axis, spec[r][axis], backs[r][axis])
+
+    run_ranks(nprocs, body)
+    torch.cuda.synchronize()
+    for axis in (0, 1, 2):
+        Xa = orc.axis_forward(x, axis)
+        num = den = 0.0
+        for r in range(nprocs):
+            ref = orc.axis_local_spectrum(Xa, n, dims, comms[r].coords, axis)
+            size, _ = plans[r].axis_size(axis)
+            assert int(np.prod(size)) == ref.size
+            got = spec[r][axis].cpu().numpy().view(cdt)[:ref.size].reshape(ref.shape)
+            num += float(np.sum(np.abs(got - ref) ** 2))
+            den += float(np.sum(np.abs(ref) ** 2))
+        assert np.sqrt(num / den) <= tol, axis
+        bl = []
+        for r in range(nprocs):
+            isz = plans[r].isize
+            bl.append(backs[r][axis].cpu().numpy().ravel()[:isz[0] * isz[1] * isz[2]].reshape(isz))
+        assert orc.rel_l2(orc.assemble_input(bl, n, dims), x * n[axis]) <= tol, axis
+    for p in plans:
+        acc.lib().accfftb_plan_destroy(p._h)
+        p._h = None
+
+
 def test_multirank_laplace_threads(cuda_device):
     torch = torch_mod()
     n, dims = (16, 20, 24), (2, 2)
@@ -496,7 +620,7 @@ def test_multirank_laplace_threads(cuda_device):
     acc.attach_local_peers(plans)
     streams = [torch.cuda.Stream() for _ in range(nprocs)]
     ins = [to_dev(orc.local_input(x, n, dims, comms[r].coords), cuda_device) for r in range(nprocs)]
-    res = {k: [torch.zeros_like(t) for t in ins] for k in ("lap", "gx", "gy", "gz", "div")}
+    res = {k: [torch.zeros_like(t) for t in ins] for k in ("lap", "gx", "gy", "gz", "div", "sx", "sy", "sz", "sdiv")}
     for r in range(nprocs):
         plans[r].set_stream(streams[r].cuda_stream)
     torch.cuda.synchronize()
@@ -506,6 +630,8 @@ def test_multirank_laplace_threads(cuda_device):
             plans[r].laplace(res["lap"][r], ins[r])
             plans[r].grad(res["gx"][r], res["gy"][r], res["gz"][r], ins[r])
             plans[r].divergence(res["div"][r], res["gx"][r], res["gy"][r], res["gz"][r])
+            plans[r].grad_slow(res["sx"][r], res["sy"][r], res["sz"][r], ins[r])
+            plans[r].divergence_slow(res["sdiv"][r], res["sx"][r], res["sy"][r], res["sz"][r])
 
     run_ranks(nprocs, body)
     torch.cuda.synchronize()
@@ -513,7 +639,9 @@ def test_multirank_laplace_threads(cuda_device):
     assert orc.rel_l2(asm("lap"), orc.laplace(x)) <= 1e-12
     for ax, k in enumerate(("gx", "gy", "gz")):
         assert orc.rel_l2(asm(k), orc.grad(x, ax)) <= 1e-12
+        assert orc.rel_l2(asm("s" + k[1]), orc.grad(x, ax)) <= 1e-12
     assert orc.rel_l2(asm("div"), orc.divergence(orc.grad(x, 0), orc.grad(x, 1), orc.grad(x, 2))) <= 1e-12
+    assert orc.rel_l2(asm("sdiv"), orc.divergence(orc.grad(x, 0), orc.grad(x, 1), orc.grad(x, 2))) <= 1e-12
     for p in plans:
         acc.lib().accfftb_plan_destroy(p._h)
         p._h = None
