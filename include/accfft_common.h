@@ -7,6 +7,7 @@
 #ifndef ACCFFT_COMMON_H
 #define ACCFFT_COMMON_H
 #include <mpi.h>
+#include <omp.h>   /* the reference's headers pull it in (include/accfft_common.h:25) and its step programs rely on that */
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
