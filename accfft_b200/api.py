@@ -85,6 +85,9 @@ def lib():
     L.accfftb_biharmonic.argtypes = [c_vp, c_vp, c_vp, c_dp]
     L.accfftb_grad.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dp]
     L.accfftb_divergence.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_dp]
+    L.accfftb_inv_laplace.argtypes = [c_vp, c_vp, c_vp, c_dp]
+    L.accfftb_inv_biharmonic.argtypes = [c_vp, c_vp, c_vp, c_dp]
+    L.accfftb_symbol_solve.argtypes = [c_vp, c_vp, c_vp, ctypes.c_double, ctypes.c_double, c_int, c_dp]
     L.accfftb_grad_slow.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dp]
     L.accfftb_divergence_slow.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_dp]
     L.accfftb_execute_r2c_axis.argtypes = [c_vp, c_int, c_vp, c_vp, c_dp]
@@ -338,6 +341,25 @@ class Plan:
         """accfft_divergence_gpu(div, Ax, Ay, Az, plan, timer)"""
         arr, p = self._timer(timer)
         _check(lib().accfftb_divergence(self._h, _ptr(Ax), _ptr(Ay), _ptr(Az), _ptr(div), p), "accfft_divergence_gpu")
+        self._timer_back(arr, timer)
+
+    def inv_laplace(self, invLA, A, timer=None):
+        """GPU twin of accfft_inv_laplace(invLA, A, plan, timer) (CPU-only in the reference, src/operators.txx:275-333)"""
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_inv_laplace(self._h, _ptr(A), _ptr(invLA), p), "accfft_inv_laplace_gpu")
+        self._timer_back(arr, timer)
+
+    def inv_biharmonic(self, invBA, A, timer=None):
+        """GPU twin of accfft_inv_biharmonic (src/operators.txx:335-392)"""
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_inv_biharmonic(self._h, _ptr(A), _ptr(invBA), p), "accfft_inv_biharmonic_gpu")
+        self._timer_back(arr, timer)
+
+    def symbol_solve(self, out, A, alpha: float, beta: float, inverse: bool, timer=None):
+        """out = F^-1[(alpha + beta |k|^2)^(+-1) F[A]]: Poisson filter (steps/step4), heat steps (steps/step6), Helmholtz"""
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_symbol_solve(self._h, _ptr(A), _ptr(out), float(alpha), float(beta), int(bool(inverse)), p),
+               "accfftb_symbol_solve")
         self._timer_back(arr, timer)
 
     def grad_slow(self, Ax, Ay, Az, A, xyz: int = 0b111, timer=None):

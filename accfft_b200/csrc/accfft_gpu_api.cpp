@@ -451,3 +451,33 @@ void accfft_divergence_slow_gpuf(float* divA, float* A_x, float* A_y, float* A_z
 void accfft_biharmonic_gpuf(float* LA, float* A, accfft_plan_gpuf* plan, double* timer) {
   accfft_biharmonic_gpu_t(LA, A, plan, timer);
 }
+
+// ---- solver-style operators (extensions; GPU twins of accfft_inv_laplace / accfft_inv_biharmonic) ------------------------
+namespace {
+template <typename T, typename Tp>
+void symbol_t(const char* what, int kind, T* out, T* A, double alpha, double beta, bool inverse, Tp* plan, double* timer) {
+  if (!baked(plan, true, what)) return;
+  int rc = kind == 0   ? accfftb_inv_laplace(plan->impl, A, out, timer)
+           : kind == 1 ? accfftb_inv_biharmonic(plan->impl, A, out, timer)
+                       : accfftb_symbol_solve(plan->impl, A, out, alpha, beta, inverse ? 1 : 0, timer);
+  report(plan->procid, what, rc);
+}
+}  // namespace
+void accfft_inv_laplace_gpu(double* invLA, double* A, accfft_plan_gpu* plan, double* timer) {
+  symbol_t("accfft_inv_laplace_gpu", 0, invLA, A, 0, 0, false, plan, timer);
+}
+void accfft_inv_biharmonic_gpu(double* invBA, double* A, accfft_plan_gpu* plan, double* timer) {
+  symbol_t("accfft_inv_biharmonic_gpu", 1, invBA, A, 0, 0, false, plan, timer);
+}
+void accfft_symbol_solve_gpu(double* out, double* A, double alpha, double beta, bool inverse, accfft_plan_gpu* plan, double* timer) {
+  symbol_t("accfft_symbol_solve_gpu", 2, out, A, alpha, beta, inverse, plan, timer);
+}
+void accfft_inv_laplace_gpuf(float* invLA, float* A, accfft_plan_gpuf* plan, double* timer) {
+  symbol_t("accfft_inv_laplace_gpuf", 0, invLA, A, 0, 0, false, plan, timer);
+}
+void accfft_inv_biharmonic_gpuf(float* invBA, float* A, accfft_plan_gpuf* plan, double* timer) {
+  symbol_t("accfft_inv_biharmonic_gpuf", 1, invBA, A, 0, 0, false, plan, timer);
+}
+void accfft_symbol_solve_gpuf(float* out, float* A, double alpha, double beta, bool inverse, accfft_plan_gpuf* plan, double* timer) {
+  symbol_t("accfft_symbol_solve_gpuf", 2, out, A, alpha, beta, inverse, plan, timer);
+}

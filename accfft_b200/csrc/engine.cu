@@ -797,6 +797,27 @@ int accfftb_biharmonic(accfftb_plan* plan, const void* A, void* BA, double* time
   return engine_finish(e, e->plan.execute_spectral(A, BA, OP_BIHARMONIC, e->spec));
 }
 
+static int spectral_impl(accfftb_plan* plan, const void* A, void* out, int op, double a, double b, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, true);
+  if (!A || !out) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  Engine* e = &plan->e;
+  int rc = ensure_spec(e);
+  if (rc) return rc;
+  TimerScope ts(e, timer, 7);
+  return engine_finish(e, e->plan.execute_spectral(A, out, op, e->spec, a, b));
+}
+
+int accfftb_inv_laplace(accfftb_plan* plan, const void* A, void* invLA, double* timer) {
+  return spectral_impl(plan, A, invLA, OP_INV_LAPLACE, 0, 0, timer);
+}
+int accfftb_inv_biharmonic(accfftb_plan* plan, const void* A, void* invBA, double* timer) {
+  return spectral_impl(plan, A, invBA, OP_INV_BIHARMONIC, 0, 0, timer);
+}
+int accfftb_symbol_solve(accfftb_plan* plan, const void* A, void* out, double alpha, double beta, int inverse, double* timer) {
+  return spectral_impl(plan, A, out, inverse ? OP_SYMBOL_INV : OP_SYMBOL_LIN, alpha, beta, timer);
+}
+
 static int grad_impl(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int comps, double* timer, bool slow) {
   const int xyz = 7;
   CHECK_PLAN(plan, true);

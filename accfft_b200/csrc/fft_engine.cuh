@@ -46,6 +46,36 @@ template <class T> ACC_HD cplx<T> cmul_mi(cplx<T> a) { return {a.y, -a.x}; }   /
 template <class T> ACC_HD cplx<T> cmul_pi(cplx<T> a) { return {-a.y, a.x}; }   // a * (+i)
 template <class T> ACC_HD cplx<T> cscale(cplx<T> a, T s) { return {a.x * s, a.y * s}; }
 
+// ---- streaming global accesses ---------------------------------------------------------------------------------
+// Every stage reads its input once and writes its output once; nothing is re-read from L2 by the same kernel.
+// ACCFFT_CACHE_HINTS bit 0: loads with evict-first (ld.global.cs), bit 1: stores with evict-first (st.global.cs).
+#ifndef ACCFFT_CACHE_HINTS
+#define ACCFFT_CACHE_HINTS 0
+#endif
+template <class T>
+ACC_HD cplx<T> ld_stream(const cplx<T>* p) {
+#if defined(__CUDA_ARCH__) && (ACCFFT_CACHE_HINTS & 1)
+  if constexpr (sizeof(T) == 8) {
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+    return {v.x, v.y};
+  } else {
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+    return {v.x, v.y};
+  }
+#else
+  return *p;
+#endif
+}
+template <class T>
+ACC_HD void st_stream(cplx<T>* p, cplx<T> v) {
+#if defined(__CUDA_ARCH__) && (ACCFFT_CACHE_HINTS & 2)
+  if constexpr (sizeof(T) == 8) __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+  else __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+#else
+  *p = v;
+#endif
+}
+
 // ---- compile-time roots of unity W_R^k = exp(-2 pi i k / R) for the in-register composites ----
 // (literal constants, 21 significant digits)
 // generic accessor through a constexpr switch so device code folds it into immediates

@@ -405,7 +405,7 @@ int Plan::execute_inverse(const void* in, void* out, bool out_padded, int xyz) {
   return 0;
 }
 
-int Plan::execute_spectral(const void* in, void* out, int op, void* spec) {
+int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double opA, double opB) {
   int rc;
   Launch z = fwd_z(in, false);
   if (!empty(z) && (rc = be->launch(z))) return rc;
@@ -417,6 +417,8 @@ int Plan::execute_spectral(const void* in, void* out, int op, void* spec) {
   // (user spectrum layout), which the inverse X stage reads back
   Launch x = fwd_x(spec);
   x.desc.op = op;
+  x.desc.opA = opA;
+  x.desc.opB = opB;
   x.desc.scale = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
   if (!empty(x) && (rc = be->launch(x))) return rc;
   Launch xi = inv_x(spec);

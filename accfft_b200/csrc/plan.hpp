@@ -117,7 +117,7 @@ struct Plan {
   int execute_forward(const void* in, void* out, bool in_padded, int xyz = 7);
   int execute_inverse(const void* in, void* out, bool out_padded, int xyz = 7);
   // fused forward -> spectral symbol -> inverse (laplace / biharmonic; src/operators_gpu.txx:280-334, :555-609)
-  int execute_spectral(const void* in, void* out, int op, void* spec);
+  int execute_spectral(const void* in, void* out, int op, void* spec, double opA = 0.0, double opB = 0.0);
   // grad (src/operators_gpu.txx:72-278): one forward into `spec` (normalised), then per selected component
   // an inverse whose X stage multiplies by i*k_axis on load.  comps: bit 0 = x, bit 1 = y, bit 2 = z.
   int execute_grad(const void* in, void* const outs[3], int comps, void* spec);

@@ -30,6 +30,13 @@ enum SpectralOp : int {
   OP_GRAD = 2,        // i * k_axis * scale          (src/operators_cuda.cu:15-112)
   OP_LAPLACE = 3,     // -(kx^2+ky^2+kz^2) * scale   (src/operators_cuda.cu:114-158)
   OP_BIHARMONIC = 4,  // (kx^2+ky^2+kz^2)^2 * scale  (src/operators_cuda.cu:160-205)
+  // solver-style symbols.  The reference has them on the CPU only (accfft_inv_laplace / accfft_inv_biharmonic,
+  // include/accfft_operators.h:57-60, src/operators.txx:275-392) or as user kernels between two transforms
+  // (steps/step4/kernels.cu:22-112 Poisson filter, steps/step6 heat step); here they ride on the X stage like the others.
+  OP_INV_LAPLACE = 5,     // scale / -(|k|^2), 0 where |k|^2 == 0      (src/operators.txx:318-327)
+  OP_INV_BIHARMONIC = 6,  // scale / |k|^4,    0 where |k|^2 == 0      (src/operators.txx:377-386)
+  OP_SYMBOL_LIN = 7,      // scale * (opA + opB |k|^2)                  (explicit heat step: 1 - dt |k|^2)
+  OP_SYMBOL_INV = 8,      // scale / (opA + opB |k|^2), 0 where the denominator is 0   (Helmholtz / implicit heat / Poisson)
 };
 
 struct StageDesc {
@@ -55,6 +62,7 @@ struct StageDesc {
   int colShift;          // strided kernels: tiles start at column -colShift so that tile origins are line aligned
                          // in a destination whose rows this rank enters at an unaligned offset (inverse Y stage)
   int inv;               // 1: inverse transform (sign +1), done as swap(re,im) . forward . swap(re,im)
+  double opA, opB;       // OP_SYMBOL_LIN / OP_SYMBOL_INV coefficients
   int staged;            // contiguous kernels with nseg > 1: outputs are collected in shared memory per destination
                          // segment and leave the CTA as bulk (TMA) copies of whole runs -- full 128-byte lines on the
                          // NVLink wire instead of one partial-line packet per warp store.  Set by the launcher.
@@ -110,7 +118,19 @@ ACC_HD cplx<T> apply_op(const StageDesc& d, cplx<T> v, int k, int a, int b) {
   const long long wy = wave_number(freq_index(d, 1, k, a, b), d.n[1]);
   const long long wz = wave_number(freq_index(d, 2, k, a, b), d.n[2]);
   const double s2 = (double)(wx * wx + wy * wy + wz * wz);
-  const double w = d.scale * (d.op == OP_LAPLACE ? -s2 : s2 * s2);
+  double w;
+  switch (d.op) {
+    case OP_LAPLACE: w = -s2; break;
+    case OP_BIHARMONIC: w = s2 * s2; break;
+    case OP_INV_LAPLACE: w = s2 == 0.0 ? 0.0 : -1.0 / s2; break;
+    case OP_INV_BIHARMONIC: w = s2 == 0.0 ? 0.0 : 1.0 / (s2 * s2); break;
+    case OP_SYMBOL_LIN: w = d.opA + d.opB * s2; break;
+    default: {
+      const double den = d.opA + d.opB * s2;
+      w = den == 0.0 ? 0.0 : 1.0 / den;
+    }
+  }
+  w *= d.scale;
   return {T(w * v.x), T(w * v.y)};
 }
 
@@ -164,7 +184,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
       if (CNT0 * G == NB0 || j < NB0) {
         const cplx<T>* p = in + (long long)j * si;
         ACC_UNROLL
-        for (int r = 0; r < R0; ++r) v[u * R0 + r] = p[r * step];
+        for (int r = 0; r < R0; ++r) v[u * R0 + r] = ld_stream(p + r * step);
       }
     }
     if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = apply_op(d, r, i, a, b); });
@@ -191,7 +211,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
         if (CNTL * G == NBL || j < NBL) {
           cplx<T>* p = out + (long long)j * so;
           ACC_UNROLL
-          for (int r = 0; r < RL; ++r) p[r * step] = v[u * RL + r];
+          for (int r = 0; r < RL; ++r) st_stream(p + r * step, v[u * RL + r]);
         }
       }
     } else {
@@ -269,7 +289,7 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
   if (valid) {
     const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB;
-    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = cswap_if(in[i], inv); });
+    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = cswap_if(ld_stream(in + i), inv); });
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   cplx<T>* stage = (cplx<T>*)ctx.smem() + ((PC * S::SMEM_ELEMS + 1) & ~1);   // only touched when d.staged
@@ -279,7 +299,7 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
       const SegDst& sd = d.seg[0];
       cplx<T>* out = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
       const long long so = sd.strideI;
-      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { out[(long long)k * so] = cswap_if(r, inv); });
+      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { st_stream(out + (long long)k * so, cswap_if(r, inv)); });
     } else if (d.staged) {
       pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { stage[staged_index<PC>(d, S::N, pcl, k)] = cswap_if(r, inv); });
     } else {
@@ -315,7 +335,7 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
   if (valid) {
     const cplx<T>* in = (const cplx<T>*)((const T*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB);
-    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = in[i]; });
+    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = ld_stream(in + i); });
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
@@ -331,7 +351,7 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
     cplx<T>* out0 = (cplx<T>*)s0.base + (long long)a * s0.strideA + (long long)b * s0.strideB;
     const long long so = s0.strideI;
     auto put = [&](int kk, cplx<T> y) {
-      if (simple) out0[(long long)kk * so] = y;
+      if (simple) st_stream(out0 + (long long)kk * so, y);
       else if (d.staged) stage[staged_index<PC>(d, M + 1, pcl, kk)] = y;
       else store_generic(d, y, kk, a, b);
     };
@@ -397,7 +417,7 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
       ACC_UNROLL
       for (int q = 0; q < NLD; ++q) {
         const int i = t + q * S::G;
-        if (i <= M) x[q] = in[i];
+        if (i <= M) x[q] = ld_stream(in + i);
       }
       if (d.op != OP_NONE) {
         ACC_UNROLL
@@ -454,7 +474,7 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
         out[nidx] = {o.x + r.y, o.y + r.x};
       });
     } else {
-      pass_foreach<S, S::NP - 1>(v, t, [&](int nidx, cplx<T>& r) { out[nidx] = cswap(r); });
+      pass_foreach<S, S::NP - 1>(v, t, [&](int nidx, cplx<T>& r) { st_stream(out + nidx, cswap(r)); });
     }
   }
 }

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(TmaCfg<T, S, TC>::THREADS, TmaCfg<T, S, TC>::C
           if (CNTL * G == NBL || j < NBL) {
             cplx<T>* p = out + (long long)j * so;
 #pragma unroll
-            for (int r = 0; r < RL; ++r) p[r * step] = v[u * RL + r];
+            for (int r = 0; r < RL; ++r) st_stream(p + r * step, v[u * RL + r]);
           }
         }
       } else {

@@ -169,6 +169,19 @@ int accfftb_execute_c2r_axis(accfftb_plan* plan, int axis, const void* data, voi
  * index 6). */
 int accfftb_laplace(accfftb_plan* plan, const void* A, void* LA, double* timer);
 int accfftb_biharmonic(accfftb_plan* plan, const void* A, void* BA, double* timer);
+/* Solver-style operators: forward transform -> symbol -> inverse transform in one call, the symbol
+ * fused into the X-pass stores like laplace (zero extra passes over the spectrum).  Wave numbers follow the same
+ * rule as every operator here (k = X > N/2 ? X - N : X, zero at X == N/2).
+ *   accfftb_inv_laplace    : u = F^-1[ -F[A] / |k|^2 ], zero mode -> 0.  GPU twin of the reference's CPU-only
+ *                            accfft_inv_laplace (include/accfft_operators.h:57-58, src/operators.txx:275-333)
+ *   accfftb_inv_biharmonic : u = F^-1[  F[A] / |k|^4 ]                   (accfft_inv_biharmonic, :59-60, :335-392)
+ *   accfftb_symbol_solve   : u = F^-1[ (alpha + beta |k|^2)^(+1 | -1) F[A] ]  (inverse != 0: divide; modes where the
+ *                            denominator vanishes -> 0).  Covers the Poisson filter of steps/step4/kernels.cu:22-112
+ *                            (alpha = 0, beta = -4 pi^2 / L^2, inverse), the explicit heat step of steps/step6
+ *                            (alpha = 1, beta = -dt, direct) and implicit / Helmholtz solves (alpha = 1, beta = dt, inverse). */
+int accfftb_inv_laplace(accfftb_plan* plan, const void* A, void* invLA, double* timer);
+int accfftb_inv_biharmonic(accfftb_plan* plan, const void* A, void* invBA, double* timer);
+int accfftb_symbol_solve(accfftb_plan* plan, const void* A, void* out, double alpha, double beta, int inverse, double* timer);
 /* xyz selects components: bit 0 = x (Ax), bit 1 = y (Ay), bit 2 = z (Az), as grad_gpu's std::bitset<3>*
  * (src/operators_gpu.txx:172-278); unselected outputs may be NULL. */
 int accfftb_grad(accfftb_plan* plan, const void* A, void* Ax, void* Ay, void* Az, int xyz, double* timer);

@@ -28,6 +28,18 @@ void accfft_divergence_slow_gpuf(float* divA, float* A_x, float* A_y, float* A_z
                                  double* timer = NULL);
 void accfft_biharmonic_gpuf(float* LA, float* A, accfft_plan_gpuf* plan, double* timer = NULL);
 
+/* GPU twins of the reference's CPU-only inverse operators (include/accfft_operators.h:57-60; src/operators.txx:275-392)
+ * and the general (alpha + beta |k|^2)^(+-1) symbol that covers the Poisson filter of steps/step4 and the heat steps of
+ * steps/step6 -- extensions: these names do not exist in the reference's GPU header. */
+void accfft_inv_laplace_gpu(double* invLA, double* A, accfft_plan_gpu* plan, double* timer = NULL);
+void accfft_inv_biharmonic_gpu(double* invBA, double* A, accfft_plan_gpu* plan, double* timer = NULL);
+void accfft_symbol_solve_gpu(double* out, double* A, double alpha, double beta, bool inverse, accfft_plan_gpu* plan,
+                             double* timer = NULL);
+void accfft_inv_laplace_gpuf(float* invLA, float* A, accfft_plan_gpuf* plan, double* timer = NULL);
+void accfft_inv_biharmonic_gpuf(float* invBA, float* A, accfft_plan_gpuf* plan, double* timer = NULL);
+void accfft_symbol_solve_gpuf(float* out, float* A, double alpha, double beta, bool inverse, accfft_plan_gpuf* plan,
+                              double* timer = NULL);
+
 template <typename T, typename Tp>
 void accfft_grad_gpu_t(T* A_x, T* A_y, T* A_z, T* A, Tp* plan, std::bitset<3>* pXYZ = NULL, double* timer = NULL);
 template <typename T, typename Tp>

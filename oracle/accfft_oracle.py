@@ -395,6 +395,45 @@ def biharmonic(x: np.ndarray) -> np.ndarray:
     return inverse_c2r(X, n) / (n[0] * n[1] * n[2])
 
 
+def _k2(n):
+    kx, ky, kz = _khat(n)
+    return kx * kx + ky * ky + kz * kz
+
+
+def inv_laplace(x: np.ndarray) -> np.ndarray:
+    """accfft_inv_laplace (CPU-only in the reference): F^-1[F[x] / -(|k|^2)], 0 where |k|^2 == 0 with the Nyquist-zeroed
+    wave numbers  (src/operators.txx:275-333: wave = -wx^2-wy^2-wz^2; wave == 0 ? 0 : 1/wave)."""
+    n = x.shape
+    k2 = _k2(n)
+    w = np.zeros_like(k2)
+    np.divide(-1.0, k2, out=w, where=k2 != 0)
+    return np.fft.irfftn(np.fft.rfftn(np.asarray(x, np.float64)) * w, s=n, axes=(0, 1, 2))
+
+
+def inv_biharmonic(x: np.ndarray) -> np.ndarray:
+    """accfft_inv_biharmonic: F^-1[F[x] / |k|^4], 0 where |k|^2 == 0  (src/operators.txx:335-392)."""
+    n = x.shape
+    k2 = _k2(n)
+    w = np.zeros_like(k2)
+    np.divide(1.0, k2 * k2, out=w, where=k2 != 0)
+    return np.fft.irfftn(np.fft.rfftn(np.asarray(x, np.float64)) * w, s=n, axes=(0, 1, 2))
+
+
+def symbol_solve(x: np.ndarray, alpha: float, beta: float, inverse: bool) -> np.ndarray:
+    """F^-1[(alpha + beta |k|^2)^(+-1) F[x]]; inverse: modes with a zero denominator -> 0.  Restates the Poisson filter
+    (steps/step4/kernels.cu:86-104, method 1: alpha = 0, beta = -4 pi^2, zero mode -> 0; note that kernel uses the plain
+    signed wave numbers without the Nyquist rule -- the operators' rule is used here, they differ only on X == N/2) and
+    the explicit heat update u + dt * laplace(u) of steps/step6/step6.cpp:150-165 (alpha = 1, beta = -dt)."""
+    n = x.shape
+    sym = alpha + beta * _k2(n)
+    if inverse:
+        w = np.zeros_like(sym)
+        np.divide(1.0, sym, out=w, where=sym != 0)
+    else:
+        w = sym
+    return np.fft.irfftn(np.fft.rfftn(np.asarray(x, np.float64)) * w, s=n, axes=(0, 1, 2))
+
+
 def divergence(ax: np.ndarray, ay: np.ndarray, az: np.ndarray) -> np.ndarray:
     """src/operators_gpu.txx:448-553: d/dx ax + d/dy ay + d/dz az."""
     return grad(ax, 0) + grad(ay, 1) + grad(az, 2)

@@ -385,6 +385,19 @@ int emu_execute_div(void* h, void** ix, void** iy, void** iz, void** out) {
   return canaries_ok(w) ? 0 : -99;
 }
 
+// solver-style symbols: op = SpectralOp value (OP_INV_LAPLACE, OP_INV_BIHARMONIC, OP_SYMBOL_LIN, OP_SYMBOL_INV)
+int emu_execute_symbol(void* h, int op, double a, double b, void** in, void** out) {
+  EmuWorld* w = (EmuWorld*)h;
+  std::vector<std::thread> th;
+  std::vector<int> rc(w->nprocs, 0);
+  for (int r = 0; r < w->nprocs; ++r)
+    th.emplace_back([&, r]() { rc[r] = w->plans[r].execute_spectral(in[r], out[r], op, w->spec[r].data(), a, b); });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w->nprocs; ++r)
+    if (rc[r]) return rc[r];
+  return canaries_ok(w) ? 0 : -99;
+}
+
 // single-axis real paths: mode 0 = r2c, 1 = c2r, 2 = derivative, 3 = derivative accumulated into out
 int emu_execute_axis(void* h, int mode, int axis, void** in, void** out) {
   EmuWorld* w = (EmuWorld*)h;

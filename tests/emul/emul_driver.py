@@ -56,6 +56,8 @@ def lib():
         _lib.emu_execute_grad.argtypes = [ctypes.c_void_p, pp, pp, pp, pp, ctypes.c_int]
         _lib.emu_execute_div.restype = ctypes.c_int
         _lib.emu_execute_div.argtypes = [ctypes.c_void_p, pp, pp, pp, pp]
+        _lib.emu_execute_symbol.restype = ctypes.c_int
+        _lib.emu_execute_symbol.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, pp, pp]
         _lib.emu_execute_axis.restype = ctypes.c_int
         _lib.emu_execute_axis.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, pp, pp]
         _lib.emu_execute_grad_axes.restype = ctypes.c_int
@@ -184,6 +186,18 @@ def _blocks_real(w, outs):
         s1 = orc.block(n[1], w.np_[1], c[1])[0]
         blocks.append(outs[r][:s0 * s1 * n[2]].reshape(s0, s1, n[2]).copy())
     return blocks
+
+
+SYMBOL_OPS = {"inv_laplace": 5, "inv_biharmonic": 6, "lin": 7, "inv": 8}
+
+
+def symbol(w, x_global, op, a=0.0, b=0.0):
+    ins = _local_real(w, x_global)
+    outs = w.alloc_out()
+    rc = lib().emu_execute_symbol(w.h, SYMBOL_OPS[op], a, b, _ptrs(ins), _ptrs(outs))
+    if rc:
+        raise RuntimeError(f"emu_execute_symbol rc={rc}")
+    return _blocks_real(w, outs)
 
 
 def axis_r2c(w, x_global, axis):

@@ -140,6 +140,26 @@ def test_grad_divergence_per_axis_scheme(n, np_):
     w.close()
 
 
+@pytest.mark.parametrize("n,np_", [((8, 8, 8), (1, 1)), ((12, 10, 16), (2, 2)), ((6, 12, 10), (3, 2)), ((9, 5, 10), (1, 2))])
+def test_solver_symbols(n, np_):
+    """inv_laplace / inv_biharmonic (CPU-only in the reference, src/operators.txx:275-392) and the general
+    (alpha + beta |k|^2)^(+-1) symbol: Poisson filter of steps/step4, heat steps of steps/step6"""
+    x = orc.synthetic_real(n, 23)
+    w = emu.World(n, np_, r2c=True)
+    asm = lambda blocks: orc.assemble_input(blocks, n, np_)
+    assert orc.rel_l2(asm(emu.symbol(w, x, "inv_laplace")), orc.inv_laplace(x)) < 1e-12
+    assert orc.rel_l2(asm(emu.symbol(w, x, "inv_biharmonic")), orc.inv_biharmonic(x)) < 1e-12
+    dt = 0.01
+    assert orc.rel_l2(asm(emu.symbol(w, x, "lin", 1.0, -dt)), x + dt * orc.laplace(x)) < 1e-12        # explicit heat step
+    assert orc.rel_l2(asm(emu.symbol(w, x, "inv", 1.0, dt)), orc.symbol_solve(x, 1.0, dt, True)) < 1e-12   # implicit heat step
+    pois = asm(emu.symbol(w, x, "inv", 0.0, -4 * np.pi ** 2))
+    assert orc.rel_l2(pois, orc.symbol_solve(x, 0.0, -4 * np.pi ** 2, True)) < 1e-12                  # Poisson, L = 1
+    # solving and re-applying the operator returns the field minus its mean and Nyquist planes
+    back = asm(emu.symbol(w, orc.inv_laplace(x), "lin", 0.0, -1.0))
+    assert orc.rel_l2(back, orc.laplace(orc.inv_laplace(x))) < 1e-12
+    w.close()
+
+
 def test_unsupported_length_is_refused():
     with pytest.raises(RuntimeError):
         emu.World((7, 8, 8), (1, 1), r2c=True)

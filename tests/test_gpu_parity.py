@@ -293,6 +293,38 @@ def test_single_axis_transforms_and_slow_operators(cuda_device, n, single):
     p.destroy()
 
 
+@pytest.mark.parametrize("n,single", [((16, 20, 24), False), ((64, 64, 64), False), ((48, 40, 36), False), ((64, 64, 64), True)])
+def test_solver_symbols_against_oracle(cuda_device, n, single):
+    """inv_laplace / inv_biharmonic (src/operators.txx:275-392, CPU-only in the reference), Poisson filter (steps/step4/kernels.cu)
+    and heat steps (steps/step6) as fused forward -> symbol -> inverse calls"""
+    torch = torch_mod()
+    rdt, _ = dtypes(single)
+    tol = 1e-12 if not single else 2e-5
+    x = orc.synthetic_real(n, 131)
+    p = make_plan(n, True, single)
+    xd = to_dev(x.astype(rdt), cuda_device)
+    o = torch.zeros_like(xd)
+    p.inv_laplace(o, xd)
+    assert orc.rel_l2(o.cpu().numpy(), orc.inv_laplace(x)) <= tol
+    p.inv_biharmonic(o, xd)
+    assert orc.rel_l2(o.cpu().numpy(), orc.inv_biharmonic(x)) <= tol
+    dt = 1.0 / n[0] / n[0] / 4      # steps/step6/step6.cpp:111
+    p.symbol_solve(o, xd, 1.0, -dt, False)
+    assert orc.rel_l2(o.cpu().numpy(), x + dt * orc.laplace(x)) <= tol
+    p.symbol_solve(o, xd, 1.0, dt, True)
+    assert orc.rel_l2(o.cpu().numpy(), orc.symbol_solve(x, 1.0, dt, True)) <= tol
+    p.symbol_solve(o, xd, 0.0, -4 * np.pi ** 2, True)
+    assert orc.rel_l2(o.cpu().numpy(), orc.symbol_solve(x, 0.0, -4 * np.pi ** 2, True)) <= tol
+    # Poisson round trip: laplace(inv_laplace(f)) == f for a zero-mean field without Nyquist content
+    f = orc.laplace(x)
+    fd = to_dev(f.astype(rdt), cuda_device)
+    u, lu = torch.zeros_like(xd), torch.zeros_like(xd)
+    p.inv_laplace(u, fd)
+    p.laplace(lu, u)
+    assert orc.rel_l2(lu.cpu().numpy(), f) <= (1e-11 if not single else 1e-3)
+    p.destroy()
+
+
 def test_full_size_per_axis_gradient_512(cuda_device):
     """BASELINE size: the fused per-axis derivative kernels against torch.fft (test-only cross-check on the device)."""
     torch = torch_mod()
