@@ -30,9 +30,11 @@ def main():
     R = n ** 3 * es
     C = n * n * (n // 2 + 1) * 2 * es
 
-    def timeit(name, fn, algo_bytes, reps=10):
+    warm = int(os.environ.get("OP_BENCH_WARMUP", "3"))
+
+    def timeit(name, fn, algo_bytes, reps=int(os.environ.get("OP_BENCH_REPS", "10"))):
         with torch.cuda.stream(stream):
-            for _ in range(3):
+            for _ in range(warm):
                 fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
