@@ -29,7 +29,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}   # BASELINE.json configs: 2x4 pencil grid on 8 GPUs
+# Process grids (the caller's c_dims in the reference: any P0 x P1 = N works).  Defaults = the fastest measured here for
+# the headline 512^3 grid (profiles/mgpu8_r05.log: 8x1 0.702 ms, 4x2 0.772, 2x4 0.786, 1x8 0.750 per round trip): a slab
+# split has ONE exchange per transform and three local stages; --grid P0xP1 selects any other (e.g. the 2x4 pencil
+# grid BASELINE.json names for its 1024^3 / uneven configs).
+GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (8, 1)}
+NVLINK_GBS = 770.0   # measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md:24-29; 900 nominal)
 
 
 def flops_per_transform(n):
@@ -149,6 +154,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512, help="grid edge (default: the headline 512)")
+    ap.add_argument("--grid", default=None, help="process grid P0xP1 (default: see GRIDS)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -174,6 +180,10 @@ def main():
     warmup = max(args.warmup, 3)
     n = (args.n, args.n, args.n)
     dims = list(GRIDS.get(world, (0, 0)))
+    if args.grid:
+        dims = [int(v) for v in args.grid.lower().split("x")]
+        if dims[0] * dims[1] != world:
+            raise SystemExit("--grid %s does not match %d ranks" % (args.grid, world))
     comm = acc.accfft_create_comm(dims, rank=rank, nprocs=world)
     plan = acc.accfft_plan_dft_3d_r2c_gpu(n, comm)
     isz, osz = plan.isize, plan.osize
@@ -325,8 +335,17 @@ def main():
                 "ms_per_launch": stages[dom]["ms"], "peak_source": peak_src}
     # whole-step view: sum of algorithmic bytes of the six passes vs the step time
     total_algo = sum(algo.values())
+    # roofline of the whole step: perfect-overlap model  T = max(HBM bytes / HBM peak, NVLink bytes out / link peak)
+    # NVLink bytes leaving this GPU per transform = the part of each exchanged array that lands on OTHER ranks
+    P0, P1 = dims
+    nvl_out = 2 * (C0 * (P1 - 1) / P1 + C1 * (P0 - 1) / P0)
+    t_hbm = total_algo / (peak * 1e9) * 1e3
+    t_nvl = nvl_out / (NVLINK_GBS * 1e9) * 1e3
     step_roof = {"algo_bytes_per_step": total_algo, "gbs": total_algo / (ms_per_step * 1e-3) / 1e9,
-                 "frac_of_hbm_peak": total_algo / (ms_per_step * 1e-3) / 1e9 / peak}
+                 "frac_of_hbm_peak": total_algo / (ms_per_step * 1e-3) / 1e9 / peak,
+                 "nvlink_bytes_out_per_step": int(nvl_out), "t_hbm_ms": t_hbm, "t_nvlink_ms": t_nvl,
+                 "t_roof_ms": max(t_hbm, t_nvl), "frac_of_roofline": max(t_hbm, t_nvl) / ms_per_step,
+                 "model": "max(HBM bytes / %.0f GB/s, NVLink bytes out / %.0f GB/s), rank 0's share" % (peak, NVLINK_GBS)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
