@@ -251,7 +251,7 @@ class Plan:
 
     def stage_kernels(self):
         """-> {stage: "plain" | "tma" | "heuristic"} for the four strided stages (see accfftb_plan_stage_variant)"""
-        names = {0: "heuristic", 1: "plain", 2: "tma"}
+        names = {0: "heuristic", 1: "plain", 2: "tma", 3: "wide"}
         return {self.PROFILE_SLOTS[s]: names.get(lib().accfftb_plan_stage_variant(self._h, s), "?") for s in (1, 2, 3, 4)}
 
     @property

@@ -161,7 +161,7 @@ struct Engine {
   int rank = 0;
   cudaStream_t stream = 0;
   bool blocking = true;
-  int tma_mode = 1;            // ACCFFT_B200_TMA: 0 = never use the TMA stage kernel, 1 = tuned / heuristic, 2 = always
+  int tma_mode = 1;            // ACCFFT_B200_TMA: 0 = plain kernel only, 1 = tuned / heuristic, 2 = TMA kernel always, 3 = wide shape always
   bool wired = false;          // peers attached (always true for single-rank plans)
   char* slab = nullptr;        // [A | B | flags] of this rank
   size_t slab_bytes = 0, bufsz = 0;
@@ -298,17 +298,29 @@ int CudaBackend::launch(const Launch& l) {
       // Two kernels serve the strided stages: the plain one and the TMA-pipelined persistent one.  Choice: the launch's
       // own request, else what plan-time tuning (ACCFFT_MEASURE) found for this stage, else a heuristic from the
       // measurements in profiles/variants_r05.txt (TMA wins when the tile's rows are a few KB apart -- the Y passes --
-      // and for single precision; the plain kernel wins on the plane-strided X passes in double).
+      // and for single precision; the plain kernel wins on the plane-strided X passes in double).  Variant 3 = the plain
+      // kernel in its wide CTA shape (kernel_cfg.hpp: CfgW).
       // Dry (plan-time) launches load BOTH; at run time the TMA kernel declines (-2) what it cannot take.
       // Stages that store to peers are NVLink-bound and want as many storing threads as possible: plain kernel
       // (profiles/mgpu8_r05.log: the one-CTA-per-SM TMA kernel lost 5-10 % there).
       int v = l.variant ? l.variant : e->variant[l.slot >= 0 && l.slot < ACCFFTB_PROFILE_SLOTS ? l.slot : 6];
-      if (v == 0) v = (l.desc.nseg == 1 && (l.desc.nA > 1 || l.prec == PREC_FLOAT)) ? 2 : 1;
+      // heuristic (ACCFFT_ESTIMATE, and every stage that stores to peers): peer stores want the longest row segments
+      // the length allows -> wide shape where it exists (else it declines and the plain kernel runs)
+      if (v == 0) v = l.desc.nseg > 1 ? 3 : ((l.desc.nA > 1 || l.prec == PREC_FLOAT) ? 2 : 1);
       if (e->tma_mode == 0) v = 1;
       if (e->tma_mode == 2) v = 2;
+      if (e->tma_mode == 3) v = 3;
       rc = -2;
       if (v == 2 || l.dry) rc = sel == 0 ? accfft_launch_k4_p0(l, e->stream) : accfft_launch_k4_p1(l, e->stream);
-      if (rc == -2 || (l.dry && rc == 0)) rc = sel == 0 ? accfft_launch_k0_p0(l, e->stream) : accfft_launch_k0_p1(l, e->stream);
+      if (rc == -2 || (l.dry && rc == 0)) {
+        Launch lv = l;
+        lv.variant = v == 3 ? 3 : 1;
+        rc = sel == 0 ? accfft_launch_k0_p0(lv, e->stream) : accfft_launch_k0_p1(lv, e->stream);
+        if (rc == -2) {   // wide shape not available for this length
+          lv.variant = 1;
+          rc = sel == 0 ? accfft_launch_k0_p0(lv, e->stream) : accfft_launch_k0_p1(lv, e->stream);
+        }
+      }
       break;
     }
     case 2: rc = accfft_launch_k1_p0(l, e->stream); break;
@@ -440,7 +452,7 @@ static int autotune(Engine* e) {
     StageDesc& d = l.desc;
     if (d.nA <= 0 || d.nB <= 0) continue;
     if (d.nseg > 1) {   // stores to peers: NVLink-bound, not tunable on this rank alone -- see CudaBackend::launch
-      e->variant[l.slot] = 1;
+      e->variant[l.slot] = 3;   // wide shape where the length has one, else the plain kernel
       continue;
     }
     // single local destination [a][k][b]: same bytes as the stage input, which fits one exchange buffer
@@ -451,8 +463,8 @@ static int autotune(Engine* e) {
     d.seg[0].strideB = 1;
     d.seg[0].strideI = d.nB;
     d.colShift = 0;
-    float best[3] = {0, 1e30f, 1e30f};
-    for (int v = 1; v <= 2 && !rc; ++v) {
+    float best[4] = {0, 1e30f, 1e30f, 1e30f};
+    for (int v = 1; v <= 3 && !rc; ++v) {
       l.variant = v;
       for (int it = 0; it < 4 && !rc; ++it) {   // first iteration = warm-up
         cudaEventRecord(a, e->stream);
@@ -467,7 +479,7 @@ static int autotune(Engine* e) {
       }
     }
     if (rc) break;
-    e->variant[l.slot] = best[2] < best[1] ? 2 : 1;
+    e->variant[l.slot] = best[2] < best[1] ? (best[3] < best[2] ? 3 : 2) : (best[3] < best[1] ? 3 : 1);
   }
   cudaEventDestroy(a);
   cudaEventDestroy(b);
@@ -610,7 +622,7 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
     cudaFuncAttributes fa;
     err = cudaFuncGetAttributes(&fa, k_barrier);
     int rc = err == cudaSuccess ? pl.prepare() : (int)err;
-    if (const char* m = getenv("ACCFFT_B200_TMA")) e->tma_mode = m[0] == '0' ? 0 : m[0] == '2' ? 2 : 1;
+    if (const char* m = getenv("ACCFFT_B200_TMA")) e->tma_mode = m[0] == '0' ? 0 : m[0] == '2' ? 2 : m[0] == '3' ? 3 : 1;
     // ACCFFT_MEASURE / ACCFFT_PATIENT: pick the faster kernel per strided stage by timing both (plan-owned buffers only)
     if (!rc && (flags & (ACCFFTB_MEASURE | ACCFFTB_PATIENT)) && e->tma_mode == 1) rc = autotune(e);
     if (rc) {

@@ -18,17 +18,30 @@ namespace accfft_b200 {
 #define ACCFFT_MAX_STRIDED_SMEM (100 * 1024)
 #endif
 
+// strided kernels: TC adjacent columns per tile; 128-byte row segments when threads / smem allow
+template <class T, class S>
+constexpr int strided_tc_pick(int max_threads, long long max_smem) {
+  int tc = 128 / (int)sizeof(cplx<T>);
+  while (tc > 1 && (S::G * tc > max_threads || (long long)S::SMEM_ELEMS * tc * (int)sizeof(cplx<T>) > max_smem)) tc /= 2;
+  return tc;
+}
+
+// "wide" CTA shape of the plain strided kernel: up to 1024 threads and 200 KB of shared memory, ONE CTA per SM.  It exists
+// for the lengths / precisions whose default shape cannot reach 128-byte row segments (threads per column G > 64 in
+// double, > 32 in single: 512 single, 768, 1024, ... -- e.g. 1024 single has 32-byte segments by default), which costs most
+// where the segments cross NVLink (profiles/mgpu8_r11.log: 290 GB/s out per GPU at 1024^3 single vs ~600 at 512^3 double).
+template <class T, class S>
+struct CfgW {
+  static constexpr int TC = strided_tc_pick<T, S>(1024, 200 * 1024);
+  static constexpr int STRIDED_THREADS = S::G * TC;
+  static constexpr int STRIDED_SMEM = S::SMEM_ELEMS * TC * (int)sizeof(cplx<T>);
+};
+
 template <class T, class S>
 struct Cfg {
-  // strided kernels: TC adjacent columns per tile; 128-byte row segments when threads / smem allow
-  static constexpr int tc_pick() {
-    int tc = 128 / (int)sizeof(cplx<T>);
-    while (tc > 1 && (S::G * tc > ACCFFT_MAX_STRIDED_THREADS ||
-                      (long long)S::SMEM_ELEMS * tc * (int)sizeof(cplx<T>) > ACCFFT_MAX_STRIDED_SMEM))
-      tc /= 2;
-    return tc;
-  }
-  static constexpr int TC = tc_pick();
+  static constexpr int TC = strided_tc_pick<T, S>(ACCFFT_MAX_STRIDED_THREADS, ACCFFT_MAX_STRIDED_SMEM);
+  // true when the wide shape has longer row segments than this one
+  static constexpr bool HAS_WIDE = CfgW<T, S>::TC > TC;
   static constexpr int STRIDED_THREADS = S::G * TC;
   static constexpr int STRIDED_SMEM = S::SMEM_ELEMS * TC * (int)sizeof(cplx<T>);
   // contiguous kernels: PC pencils per CTA, about ACCFFT_CONTIG_THREADS threads

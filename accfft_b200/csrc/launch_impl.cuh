@@ -38,6 +38,12 @@ __global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS) k_strided_c2c(cons
   CudaCtx ctx;
   strided_c2c_body<T, S, Cfg<T, S>::TC>(d, ctx);
 }
+// same body, wide CTA shape (kernel_cfg.hpp: CfgW); instantiated only where it differs from the default shape
+template <class T, class S>
+__global__ void __launch_bounds__(CfgW<T, S>::STRIDED_THREADS, 1) k_strided_c2c_wide(const __grid_constant__ StageDesc d) {
+  CudaCtx ctx;
+  strided_c2c_body<T, S, CfgW<T, S>::TC>(d, ctx);
+}
 template <class T, class S>
 __global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_c2c(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
@@ -115,6 +121,16 @@ static int launch_one(const Launch& l, cudaStream_t st) {
   const StageDesc& d = l.desc;
 #endif
 #if ACCFFT_KIND == 0
+  if constexpr (C::HAS_WIDE) {
+    using W = CfgW<T, S>;
+    if (l.dry || l.variant == 3) {
+      const long long nbw = (long long)d.nA * ((d.nB + d.colShift + W::TC - 1) / W::TC);
+      const int rc = launch_kernel(k_strided_c2c_wide<T, S>, nbw, W::STRIDED_THREADS, W::STRIDED_SMEM, d, st, l.dry);
+      if (!l.dry || rc) return rc;
+    }
+  } else if (l.variant == 3 && !l.dry) {
+    return -2;   // no wide shape for this length / precision: the caller falls back to the default shape
+  }
   const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
   return launch_kernel(k_strided_c2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
 #elif ACCFFT_KIND >= 5

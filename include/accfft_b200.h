@@ -117,7 +117,9 @@ int accfftb_plan_set_profiling(accfftb_plan* plan, int on);
 int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOTS], long long count[ACCFFTB_PROFILE_SLOTS]);
 
 /* Which kernel serves a strided stage (slot 1 forward Y, 2 forward X, 3 inverse X, 4 inverse Y): 1 = plain kernel,
- * 2 = TMA-pipelined persistent kernel, 0 = decided per launch by the size heuristic (plans made with ACCFFTB_ESTIMATE).
+ * 2 = TMA-pipelined persistent kernel, 3 = plain kernel in its wide CTA shape (up to 1024 threads: 128-byte row segments
+ * for lengths / precisions whose default shape cannot reach them; used for every stage that stores to peers, falls back to
+ * 1 where the length has no wide shape), 0 = decided per launch by the size heuristic (plans made with ACCFFTB_ESTIMATE).
  * Plans made with ACCFFTB_MEASURE / ACCFFTB_PATIENT time both at creation -- on plan-owned scratch, never on user
  * data (the reference's tuner, src/transpose_gpu.cpp:632-743, runs on the caller's buffers) -- and keep the faster. */
 int accfftb_plan_stage_variant(const accfftb_plan* plan, int slot);

@@ -6,15 +6,18 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     sys.path.insert(0, ROOT)
     import torch
     import accfft_b200 as acc
-    n = int(os.environ.get("VAR_N", "512"))
+    nn = [int(v) for v in os.environ.get("VAR_N", "512").split(",")]
+    n3 = tuple(nn) if len(nn) == 3 else (nn[0],) * 3
+    n = n3[0]
     kind = os.environ.get("VAR_KIND", "r2c")
     single = os.environ.get("VAR_SINGLE", "0") == "1"
     torch.cuda.set_device(0)
     comm = acc.Comm(0, 1, (1, 1))
-    p = acc.Plan((n, n, n), comm, r2c=(kind == "r2c"), single=single)
+    p = acc.Plan(n3, comm, r2c=(kind == "r2c"), single=single)
     rdt = torch.float32 if single else torch.float64
     es = 4 if single else 8
-    x = torch.rand(n * n * n * (1 if kind == "r2c" else 2), dtype=rdt, device="cuda")
+    ntot = n3[0] * n3[1] * n3[2]
+    x = torch.rand(ntot * (1 if kind == "r2c" else 2), dtype=rdt, device="cuda")
     out = torch.zeros(p.alloc_max // es, dtype=rdt, device="cuda")
     back = torch.zeros_like(x)
     st = torch.cuda.Stream()
@@ -35,14 +38,16 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         e1.record(st)
     torch.cuda.synchronize()
     prof = p.profile_read()
-    err = float(torch.linalg.vector_norm(back / n**3 - x) / torch.linalg.vector_norm(x))
-    print(json.dumps({"lib": os.path.basename(os.environ.get("ACCFFT_B200_LIB", "")), "tma": os.environ.get("ACCFFT_B200_TMA", "1"), "n": n, "kind": kind, "single": single,
+    err = float(torch.linalg.vector_norm(back / ntot - x) / torch.linalg.vector_norm(x))
+    print(json.dumps({"lib": os.path.basename(os.environ.get("ACCFFT_B200_LIB", "")), "tma": os.environ.get("ACCFFT_B200_TMA", "1"), "n": list(n3), "kind": kind, "kernels": p.stage_kernels(), "single": single,
                       "ms_step": e0.elapsed_time(e1) / iters, "err": err,
                       "stages": {k: round(v[0] / max(v[1], 1), 4) for k, v in prof.items() if v[1]}}))
     sys.exit(0)
 CASES = (("r2c", 512, "0"), ("c2c", 512, "0"), ("r2c", 256, "0"), ("r2c", 512, "1"))
 if os.environ.get("VAR_QUICK"):
     CASES = CASES[:1]
+if os.environ.get("VAR_CASES"):   # e.g. "r2c:512:1;r2c:768,768,384:0"
+    CASES = tuple(tuple(c.split(":")) for c in os.environ["VAR_CASES"].split(";"))
 for spec in sys.argv[1:]:
     # "path/to/lib.so" or "path/to/lib.so:ENV=VAL,ENV2=VAL2"
     lib, _, extra = spec.partition(":")

@@ -51,12 +51,12 @@ def make_plan(n, r2c, single, comm=None, **kw):
     return acc.Plan(n, comm, r2c=r2c, single=single, **kw)
 
 
-@pytest.fixture(params=["tuned", "plain", "tma"])
+@pytest.fixture(params=["tuned", "plain", "tma", "wide"])
 def stage_kernels(request, monkeypatch):
     """The strided (Y / X) stages have two kernels: the plain one and the TMA-pipelined persistent one.  Run the
     parity tests under plan-time tuning (ACCFFT_MEASURE, the reference's default flag), and with each kernel forced
     (ACCFFT_B200_TMA is read when a plan is created)."""
-    monkeypatch.setenv("ACCFFT_B200_TMA", {"tuned": "1", "plain": "0", "tma": "2"}[request.param])
+    monkeypatch.setenv("ACCFFT_B200_TMA", {"tuned": "1", "plain": "0", "tma": "2", "wide": "3"}[request.param])
     return acc.ACCFFT_MEASURE if request.param == "tuned" else acc.ACCFFT_ESTIMATE
 
 
