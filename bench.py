@@ -30,10 +30,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # Process grids (the caller's c_dims in the reference: any P0 x P1 = N works).  Defaults = the fastest measured here for
-# the headline 512^3 grid (profiles/mgpu8_r05.log: 8x1 0.702 ms, 4x2 0.772, 2x4 0.786, 1x8 0.750 per round trip): a slab
+# the headline 512^3 grid (profiles/mgpu8_r14.log: 8x1 0.696 ms, 4x2 0.764, 2x4 0.771, 1x8 0.765 per round trip;
+# profiles/mgpu4_r15.log: 4x1 1.111, 2x2 1.134, 1x4 1.153): a slab
 # split has ONE exchange per transform and three local stages; --grid P0xP1 selects any other (e.g. the 2x4 pencil
 # grid BASELINE.json names for its 1024^3 / uneven configs).
-GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (8, 1)}
+GRIDS = {1: (1, 1), 2: (2, 1), 4: (4, 1), 8: (8, 1)}
 NVLINK_GBS = 770.0   # measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md:24-29; 900 nominal)
 
 
@@ -314,6 +315,9 @@ def main():
     if world > 1:      # the stage that feeds an exchange writes the NEXT layout's bytes (same totals on even grids)
         algo["fwd_z"] = R + C0
     peak, peak_src = measured_peaks()
+    # bytes each stage stores into OTHER ranks' buffers over NVLink (the exchange is fused into the stage's stores)
+    nvl = {"fwd_z": C0 * (dims[1] - 1) / dims[1], "fwd_y": C1 * (dims[0] - 1) / dims[0],
+           "inv_x": C2 * (dims[0] - 1) / dims[0], "inv_y": C0 * (dims[1] - 1) / dims[1]}
     stages = {}
     for k, (tms, cnt) in prof.items():
         if cnt:
@@ -321,6 +325,9 @@ def main():
             if k in algo:
                 stages[k]["algo_bytes"] = algo[k]
                 stages[k]["gbs"] = algo[k] / (tms / cnt * 1e-3) / 1e9
+            if nvl.get(k):
+                stages[k]["nvlink_out_bytes"] = int(nvl[k])
+                stages[k]["nvlink_out_gbs"] = nvl[k] / (tms / cnt * 1e-3) / 1e9
     dom = max((k for k in stages if k in algo), key=lambda k: stages[k]["ms"] * stages[k]["launches_per_step"])
     traffic = None
     try:
@@ -333,6 +340,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": stages[dom]["gbs"] / peak, "traffic": traffic, "algo_bytes_per_launch": algo[dom],
                 "ms_per_launch": stages[dom]["ms"], "peak_source": peak_src}
+    if "nvlink_out_gbs" in stages[dom]:   # the dominant kernel stores to peers: its ceiling is the link, not HBM
+        roofline.update({"nvlink_out_gbs": stages[dom]["nvlink_out_gbs"], "nvlink_peak_gbs": NVLINK_GBS,
+                         "nvlink_frac": stages[dom]["nvlink_out_gbs"] / NVLINK_GBS,
+                         "note": "this stage's stores cross NVLink (exchange fused into the FFT kernel): NVLink-bound, see nvlink_frac"})
     # whole-step view: sum of algorithmic bytes of the six passes vs the step time
     total_algo = sum(algo.values())
     # roofline of the whole step: perfect-overlap model  T = max(HBM bytes / HBM peak, NVLink bytes out / link peak)
