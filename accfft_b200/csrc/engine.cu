@@ -149,6 +149,12 @@ struct CudaBackend : Backend {
   const void* twiddle(Prec prec, int tableN) override;
   int launch(const Launch& l) override;
   int barrier() override;
+  int pipeline_chunks() override;
+  int fork() override;
+  int hand(int from) override;
+  int join() override;
+  int barrier_on(int lane) override;
+  int link(cudaStream_t from, cudaStream_t to);
 };
 
 constexpr size_t kFlagBytes = 4096;
@@ -161,6 +167,10 @@ struct Engine {
   int rank = 0;
   cudaStream_t stream = 0;
   bool blocking = true;
+  cudaStream_t aux = nullptr;  // lane 1 of software-pipelined stages (lowest priority: its kernels wait on NVLink anyway)
+  int overlap_chunks = 1;      // ACCFFT_B200_OVERLAP: chunks of the pipelined Z/Y stages on slab grids (<= 1: off)
+  std::vector<cudaEvent_t> sync_events;   // ring of timing-less events for fork / hand / join
+  size_t sync_next = 0;
   int tma_mode = 1;            // ACCFFT_B200_TMA: 0 = plain kernel only, 1 = tuned / heuristic, 2 = TMA kernel always, 3 = wide shape always
   bool wired = false;          // peers attached (always true for single-rank plans)
   char* slab = nullptr;        // [A | B | flags] of this rank
@@ -259,8 +269,39 @@ struct ScopedTimer {
   }
 };
 
+// everything below enqueues on e->stream; a launch on lane 1 swaps the auxiliary stream in for its duration
+struct LaneScope {
+  Engine* e;
+  cudaStream_t saved;
+  LaneScope(Engine* e_, int lane) : e(e_), saved(e_->stream) {
+    if (lane == 1 && e->aux) e->stream = e->aux;
+  }
+  ~LaneScope() { e->stream = saved; }
+};
+
+int CudaBackend::pipeline_chunks() { return (e->timing || !e->aux) ? 1 : e->overlap_chunks; }
+
+int CudaBackend::link(cudaStream_t from, cudaStream_t to) {
+  if (e->sync_events.empty()) {
+    e->sync_events.resize(64, nullptr);
+    for (auto& ev : e->sync_events) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  cudaEvent_t ev = e->sync_events[e->sync_next++ % e->sync_events.size()];
+  CU(cudaEventRecord(ev, from));
+  CU(cudaStreamWaitEvent(to, ev, 0));
+  return 0;
+}
+int CudaBackend::fork() { return link(e->stream, e->aux); }
+int CudaBackend::hand(int from) { return from == 0 ? link(e->stream, e->aux) : link(e->aux, e->stream); }
+int CudaBackend::join() { return link(e->aux, e->stream); }
+int CudaBackend::barrier_on(int lane) {
+  LaneScope ls(e, lane);
+  return barrier();
+}
+
 int CudaBackend::launch(const Launch& l) {
   if (!l.desc.tw && l.kind != K_COPY_REAL) return fail(ACCFFTB_ERR_STATE, "twiddle table allocation failed");
+  LaneScope lane_scope(e, l.dry ? 0 : l.lane);
   ScopedTimer tm(e, l.dry ? nullptr : &e->t_fft);
   ScopedProfile pf(e, l.dry ? -1 : l.slot);
   int rc = -1;
@@ -380,6 +421,9 @@ static void engine_free(Engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  if (e->aux) cudaStreamSynchronize(e->aux), cudaStreamDestroy(e->aux);
+  for (auto ev : e->sync_events)
+    if (ev) cudaEventDestroy(ev);
   for (void* p : e->opened) cudaIpcCloseMemHandle(p);
   for (auto& kv : e->tables) cudaFree(kv.second);
   if (e->slab) cudaFree(e->slab);
@@ -622,6 +666,12 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
     cudaFuncAttributes fa;
     err = cudaFuncGetAttributes(&fa, k_barrier);
     int rc = err == cudaSuccess ? pl.prepare() : (int)err;
+    if (const char* m = getenv("ACCFFT_B200_OVERLAP")) e->overlap_chunks = atoi(m);
+    if (pl.nprocs > 1 && e->overlap_chunks > 1) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least priority (numerically greatest)
+      if (cudaStreamCreateWithPriority(&e->aux, cudaStreamNonBlocking, lo) != cudaSuccess) e->aux = nullptr, cudaGetLastError();
+    }
     if (const char* m = getenv("ACCFFT_B200_TMA")) e->tma_mode = m[0] == '0' ? 0 : m[0] == '2' ? 2 : m[0] == '3' ? 3 : 1;
     // ACCFFT_MEASURE / ACCFFT_PATIENT: pick the faster kernel per strided stage by timing both (plan-owned buffers only)
     if (!rc && (flags & (ACCFFTB_MEASURE | ACCFFTB_PATIENT)) && e->tma_mode == 1) rc = autotune(e);

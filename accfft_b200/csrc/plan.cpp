@@ -373,8 +373,52 @@ static void no_transform(Launch& l, int n_axis) {
   l.fftN = n_axis;
 }
 
+// restrict a stage to the outer indices [a0, a0 + na): input and every destination advance by a0 outer strides
+static Launch restrict_a(Launch l, int a0, int na, size_t in_elem, size_t out_elem) {
+  StageDesc& d = l.desc;
+  d.in = (const char*)d.in + (long long)a0 * d.inStrideA * (long long)in_elem;
+  for (int s = 0; s < d.nseg; ++s) d.seg[s].base = (char*)d.seg[s].base + (long long)a0 * d.seg[s].strideA * (long long)out_elem;
+  d.nA = na;
+  return l;
+}
+
+// Slab grids (P1 == 1): Z writes only this rank's A and Y is the stage whose stores cross NVLink, so the two can be
+// software-pipelined over chunks of the outer index i0 with no extra synchronisation between ranks: chunk c of Y (lane 1,
+// NVLink-bound) runs while chunk c+1 of Z (lane 0, HBM-bound) computes.  The barrier that opens the operation for writes
+// into the peers' B ("B is never written before the first barrier of an operation") moves to lane 1, where
+// it overlaps the first Z chunk instead of waiting in front of it.
+int Plan::forward_zy_pipelined(const void* in, bool in_padded, int nch) {
+  int rc;
+  const size_t cs = prec == PREC_DOUBLE ? 16 : 8;
+  const size_t in_elem = g.r2c ? cs / 2 : cs;
+  const Launch z = fwd_z(in, in_padded), y = fwd_y();
+  const int n = g.i0.size;
+  if (nch > n) nch = n > 0 ? n : 1;
+  if ((rc = be->fork())) return rc;
+  if ((rc = be->barrier_on(1))) return rc;
+  for (int c = 0; c < nch; ++c) {
+    const int a0 = (int)((long long)n * c / nch), a1 = (int)((long long)n * (c + 1) / nch);
+    if (a1 <= a0) continue;
+    Launch zc = restrict_a(z, a0, a1 - a0, in_elem, cs);
+    zc.lane = 0;
+    if (!empty(zc) && (rc = be->launch(zc))) return rc;
+    if ((rc = be->hand(0))) return rc;
+    Launch yc = restrict_a(y, a0, a1 - a0, cs, cs);
+    yc.lane = 1;
+    if (!empty(yc) && (rc = be->launch(yc))) return rc;
+  }
+  return be->join();
+}
+
 int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
   int rc;
+  if (xyz == 7 && nprocs > 1 && g.np[1] == 1 && be->pipeline_chunks() > 1) {
+    if ((rc = forward_zy_pipelined(in, in_padded, be->pipeline_chunks()))) return rc;
+    if ((rc = be->barrier())) return rc;
+    Launch x = fwd_x(out);
+    if (!empty(x) && (rc = be->launch(x))) return rc;
+    return 0;
+  }
   Launch z = fwd_z(in, in_padded);
   if (!(xyz & 4)) no_transform(z, g.n[2]);
   if (!empty(z) && (rc = be->launch(z))) return rc;

@@ -28,6 +28,7 @@ struct Launch {
   int slot;        // profiling slot: 0 fwd Z, 1 fwd Y, 2 fwd X, 3 inv X, 4 inv Y, 5 inv Z  (6 = barrier),
                    // 7 = real copy / exchange stages, 8 = single-axis real transform / derivative stages
   long long copyN; // K_COPY_REAL: extent of the fastest input index k (a flat plane index on the x path)
+  int lane;        // 0 = the plan's stream, 1 = the plan's auxiliary stream (software-pipelined stages, see Backend::fork)
   int variant;     // strided stages: 0 = backend's choice (plan-time tuning / heuristic), 1 = plain kernel, 2 = TMA-pipelined kernel
   StageDesc desc;
 };
@@ -40,6 +41,18 @@ struct Backend {
   virtual const void* twiddle(Prec prec, int tableN) = 0;   // W_tableN[k], k < tableN
   virtual int launch(const Launch& l) = 0;                   // enqueue on the plan's stream; 0 = ok
   virtual int barrier() = 0;                                 // all ranks of the comm, stream ordered
+  // Two-lane software pipelining of adjacent stages (lane 0 = the plan's stream, lane 1 = an auxiliary stream):
+  //   pipeline_chunks()  how many chunks the backend wants (<= 1: run the stages back to back on lane 0)
+  //   fork()             lane 1 waits for everything enqueued on lane 0 so far
+  //   hand(from)         the OTHER lane waits for everything enqueued on lane `from` so far
+  //   join()             lane 0 waits for lane 1
+  //   barrier_on(lane)   the inter-rank barrier enqueued on that lane
+  // Backends without streams (the CPU emulator) execute in program order, which satisfies every dependency.
+  virtual int pipeline_chunks() { return 1; }
+  virtual int fork() { return 0; }
+  virtual int hand(int) { return 0; }
+  virtual int join() { return 0; }
+  virtual int barrier_on(int) { return barrier(); }
 };
 
 struct Geometry {
@@ -115,6 +128,8 @@ struct Plan {
   // an axis whose bit is clear is not transformed, but its stage still moves the data into the next layout, exactly
   // as the reference always runs its transposes.  r2c / c2r need the Z bit (the real <-> complex step).
   int execute_forward(const void* in, void* out, bool in_padded, int xyz = 7);
+  // slab grids (P1 == 1): the local Z stage and the exchanging Y stage software-pipelined over chunks of i0
+  int forward_zy_pipelined(const void* in, bool in_padded, int nch);
   int execute_inverse(const void* in, void* out, bool out_padded, int xyz = 7);
   // fused forward -> spectral symbol -> inverse (laplace / biharmonic; src/operators_gpu.txx:280-334, :555-609)
   int execute_spectral(const void* in, void* out, int op, void* spec, double opA = 0.0, double opB = 0.0);

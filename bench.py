@@ -324,10 +324,10 @@ def main():
             stages[k] = {"ms": tms / cnt, "launches_per_step": cnt / args.steps}
             if k in algo:
                 stages[k]["algo_bytes"] = algo[k]
-                stages[k]["gbs"] = algo[k] / (tms / cnt * 1e-3) / 1e9
+                stages[k]["gbs"] = algo[k] / (tms / args.steps * 1e-3) / 1e9     # per-step bytes / per-step time
             if nvl.get(k):
                 stages[k]["nvlink_out_bytes"] = int(nvl[k])
-                stages[k]["nvlink_out_gbs"] = nvl[k] / (tms / cnt * 1e-3) / 1e9
+                stages[k]["nvlink_out_gbs"] = nvl[k] / (tms / args.steps * 1e-3) / 1e9
     dom = max((k for k in stages if k in algo), key=lambda k: stages[k]["ms"] * stages[k]["launches_per_step"])
     traffic = None
     try:
@@ -338,7 +338,8 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["gbs"] / peak, "traffic": traffic, "algo_bytes_per_launch": algo[dom],
+                "frac": stages[dom]["gbs"] / peak, "traffic": traffic,
+                "algo_bytes_per_launch": algo[dom] / stages[dom]["launches_per_step"],
                 "ms_per_launch": stages[dom]["ms"], "peak_source": peak_src}
     if "nvlink_out_gbs" in stages[dom]:   # the dominant kernel stores to peers: its ceiling is the link, not HBM
         roofline.update({"nvlink_out_gbs": stages[dom]["nvlink_out_gbs"], "nvlink_peak_gbs": NVLINK_GBS,

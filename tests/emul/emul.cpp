@@ -238,6 +238,12 @@ struct EmuBackend : Backend {
     return 0;
   }
   int barrier() override;
+  // software-pipelined stages: the emulator executes in program order, which satisfies every fork / hand / join
+  // dependency, so only the chunked descriptors (Plan::forward_zy_pipelined) are exercised here
+  int pipeline_chunks() override {
+    const char* c = getenv("EMU_PIPELINE_CHUNKS");
+    return c ? atoi(c) : 1;
+  }
 };
 
 struct EmuWorld {

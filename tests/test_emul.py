@@ -160,6 +160,24 @@ def test_solver_symbols(n, np_):
     w.close()
 
 
+@pytest.mark.parametrize("n,np_,r2c", [((8, 8, 8), (2, 1), True), ((12, 10, 16), (3, 1), True), ((5, 6, 6), (4, 1), True),
+                                       ((16, 12, 6), (2, 1), False), ((32, 24, 20), (4, 1), True), ((12, 10, 16), (2, 2), True)])
+@pytest.mark.parametrize("chunks", [2, 3, 7])
+def test_pipelined_slab_forward(n, np_, r2c, chunks, monkeypatch):
+    """slab grids (P1 == 1): the Z and Y stages run as chunks of i0 (Plan::forward_zy_pipelined); same spectrum.
+    (2, 2) is not a slab: the chunk count must be ignored there."""
+    monkeypatch.setenv("EMU_PIPELINE_CHUNKS", str(chunks))
+    x = orc.synthetic_real(n, 29) if r2c else orc.synthetic_complex(n, 29)
+    X = orc.forward_r2c(x) if r2c else orc.forward_c2c(x)
+    w = emu.World(n, np_, r2c=r2c)
+    for _ in range(2):
+        assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_, r2c=r2c), X) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, np_), x * x.size) < 1e-12
+    if r2c:
+        assert orc.rel_l2(orc.assemble_output(w.forward(x, padded=True), n, np_), X) < 1e-12
+    w.close()
+
+
 def test_unsupported_length_is_refused():
     with pytest.raises(RuntimeError):
         emu.World((7, 8, 8), (1, 1), r2c=True)
