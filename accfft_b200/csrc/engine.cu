@@ -38,6 +38,8 @@ int accfft_launch_k6_p0(const Launch&, cudaStream_t);
 int accfft_launch_k6_p1(const Launch&, cudaStream_t);
 int accfft_launch_k7_p0(const Launch&, cudaStream_t);
 int accfft_launch_k7_p1(const Launch&, cudaStream_t);
+int accfft_launch_k8_p0(const Launch&, cudaStream_t);   // contiguous (Z-axis) derivative
+int accfft_launch_k8_p1(const Launch&, cudaStream_t);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -376,6 +378,8 @@ int CudaBackend::launch(const Launch& l) {
     case 13: rc = accfft_launch_k6_p1(l, e->stream); break;
     case 14: rc = accfft_launch_k7_p0(l, e->stream); break;
     case 15: rc = accfft_launch_k7_p1(l, e->stream); break;
+    case 18: rc = accfft_launch_k8_p0(l, e->stream); break;   // K_CONTIG_DERIV = 9
+    case 19: rc = accfft_launch_k8_p1(l, e->stream); break;
     default: break;
   }
   if (rc == -1) return fail(ACCFFTB_ERR_UNSUPPORTED, "no kernel schedule for length " + std::to_string(l.fftN));
@@ -899,7 +903,7 @@ static int div_impl(accfftb_plan* plan, const void* Ax, const void* Ay, const vo
   const int xyz = 7;
   CHECK_PLAN(plan, true);
   if (!Ax || !Ay || !Az || !div) return fail(ACCFFTB_ERR_ARG, "null data pointer");
-  if (!slow && (div == Ay || div == Az)) return fail(ACCFFTB_ERR_ARG, "divergence output must not alias an input component");
+  if (!slow && (div == Ax || div == Ay || div == Az)) return fail(ACCFFTB_ERR_ARG, "divergence output must not alias an input component");
   Engine* e = &plan->e;
   int rc = ensure_spec(e);
   if (rc) return rc;

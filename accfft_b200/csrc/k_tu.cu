@@ -2,7 +2,8 @@
 // kernels of that kind / precision for every schedule and exports one launcher.
 //   ACCFFT_KIND: 0 strided c2c (Y and X passes), 1 contiguous c2c (Z pass of c2c plans),
 //                2 contiguous r2c, 3 contiguous c2r (Z pass of r2c plans), 4 TMA-pipelined strided c2c,
-//                5 strided r2c, 6 strided c2r, 7 strided spectral derivative (single-axis real paths, stage_real.cuh)
+//                5 strided r2c, 6 strided c2r, 7 strided spectral derivative (single-axis real paths, stage_real.cuh),
+//                8 contiguous (Z-axis) spectral derivative
 //   ACCFFT_PREC: 0 double, 1 float
 #include "launch_impl.cuh"
 

@@ -80,6 +80,12 @@ __global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS, ACCFFT_REAL_MINB) 
   strided_deriv_body<T, S, Cfg<T, S>::TC>(d, ctx);
 }
 
+template <class T, class S>
+__global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_deriv(const __grid_constant__ StageDesc d) {
+  CudaCtx ctx;
+  contig_deriv_body<T, S, Cfg<T, S>::PC>(d, ctx);
+}
+
 template <class K>
 static int launch_kernel(K kernel, long long nblocks, int threads, int smem, const StageDesc& d, cudaStream_t st,
                          bool dry) {
@@ -133,6 +139,9 @@ static int launch_one(const Launch& l, cudaStream_t st) {
   }
   const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
   return launch_kernel(k_strided_c2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
+#elif ACCFFT_KIND == 8
+  const long long npairs = ((long long)d.nA * d.nB + 1) / 2;
+  return launch_kernel(k_contig_deriv<T, S>, (npairs + C::PC - 1) / C::PC, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
 #elif ACCFFT_KIND >= 5
   const long long nb = (long long)d.nA * ((d.nB + 2 * C::TC - 1) / (2 * C::TC));
 #if ACCFFT_KIND == 5

@@ -15,7 +15,8 @@ namespace accfft_b200 {
 enum Kind : int {
   K_STRIDED_C2C = 0, K_CONTIG_C2C = 1, K_CONTIG_R2C = 2, K_CONTIG_C2R = 3, K_COPY = 4,
   // real transforms along a strided axis (stage_real.cuh): the single-axis executes and the per-axis derivative
-  K_STRIDED_R2C = 5, K_STRIDED_C2R = 6, K_STRIDED_DERIV = 7, K_COPY_REAL = 8
+  K_STRIDED_R2C = 5, K_STRIDED_C2R = 6, K_STRIDED_DERIV = 7, K_COPY_REAL = 8,
+  K_CONTIG_DERIV = 9   // fused derivative along the contiguous (Z) axis: launcher translation unit k8
 };
 enum Prec : int { PREC_DOUBLE = 0, PREC_FLOAT = 1 };
 

@@ -193,6 +193,59 @@ ACC_HD void strided_deriv_body(const StageDesc& d, Ctx& ctx) {
 }
 
 // ================================================================================================
+// contiguous spectral derivative (Z axis): two ADJACENT PENCILS (rows of N real values) form one complex row
+// z[n] = row_p[n] + i row_(p+1)[n]; forward passes -> symbol -> inverse passes -> real parts back to row_p, imaginary parts to
+// row_(p+1).  One read and one write of the field instead of r2c + multiply + c2r (src/operators_gpu.txx:264-276: three
+// kernels, four array passes).  PC pencil PAIRS per CTA, S::G threads per pair; S is the schedule of the FULL length N2.
+// Strides in real elements; loads / stores are scalar and coalesced along n.
+// ================================================================================================
+template <class T, class S, int PC, class Ctx>
+ACC_HD void contig_deriv_body(const StageDesc& d, Ctx& ctx) {
+  const int tid = ctx.tid();
+  const int t = tid % S::G, pcl = tid / S::G;
+  const long long total = (long long)d.nA * d.nB;                 // pencils
+  const long long p0 = 2 * (ctx.bid() * PC + pcl), p1 = p0 + 1;   // this thread group's two pencils
+  const bool valid0 = p0 < total, valid1 = p1 < total;
+  const int a0 = valid0 ? (int)(p0 / d.nB) : 0, b0 = valid0 ? (int)(p0 % d.nB) : 0;
+  const int a1 = valid1 ? (int)(p1 / d.nB) : 0, b1 = valid1 ? (int)(p1 % d.nB) : 0;
+  cplx<T> w1[S::NTW];
+  load_base_twiddles<S, 1>(w1, t, (const cplx<T>*)d.tw);
+  cplx<T> v[S::NREG];
+  ACC_UNROLL
+  for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
+  if (valid0) {
+    const T* r0 = (const T*)d.in + (long long)a0 * d.inStrideA + (long long)b0 * d.inStrideB;
+    const T* r1 = (const T*)d.in + (long long)a1 * d.inStrideA + (long long)b1 * d.inStrideB;
+    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = {r0[i], valid1 ? r1[i] : T(0)}; });
+  }
+  cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
+  auto addr = [&](int i) { return sm + S::phys(i); };
+  fft_passes<S>(v, t, w1, addr, [&]() { ctx.sync(); });
+  constexpr bool kSameOrder = S::radix(0) == S::radix(S::NP - 1);
+  if constexpr (kSameOrder) {
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(apply_op(d, r, k, a0, b0)); });
+    if constexpr (S::NP > 1) ctx.sync();
+  } else {
+    if constexpr (S::NP > 1) ctx.sync();
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(apply_op(d, r, k, a0, b0)); });
+    ctx.sync();
+    pass_gather<S, 0>(v, t, addr);
+    if constexpr (S::NP > 1) ctx.sync();
+  }
+  fft_passes<S>(v, t, w1, addr, [&]() { ctx.sync(); });
+  if (valid0) {
+    const SegDst& sd = d.seg[0];
+    T* o0 = (T*)sd.base + (long long)a0 * sd.strideA + (long long)b0 * sd.strideB;
+    T* o1 = (T*)sd.base + (long long)a1 * sd.strideA + (long long)b1 * sd.strideB;
+    const bool acc = d.accumulate != 0;
+    pass_foreach<S, S::NP - 1>(v, t, [&](int n, cplx<T>& r) {   // r holds the swapped result: (im, re)
+      o0[n] = acc ? T(o0[n] + r.y) : r.y;
+      if (valid1) o1[n] = acc ? T(o1[n] + r.x) : r.x;
+    });
+  }
+}
+
+// ================================================================================================
 // real copy stage: element (a, b, k) of the input goes to segment k / blk (the real-data transposes T_plan_y / T_plan_x
 // and their inverses, src/accfft_gpu.cpp:369-373, :426-438, and the D2D copies around them, :1357, :1407, :1509, :1543).
 // One call = one element; the launchers walk the index space with k fastest.

@@ -145,6 +145,11 @@ static void emu_launch_sched(const Launch& l) {
       run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2r_body<T, S, C::PC>(d, c); });
       break;
     }
+    case K_CONTIG_DERIV: {
+      const long long npairs = ((long long)d.nA * d.nB + 1) / 2;
+      run_grid((npairs + C::PC - 1) / C::PC, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_deriv_body<T, S, C::PC>(d, c); });
+      break;
+    }
     case K_STRIDED_R2C:
     case K_STRIDED_C2R:
     case K_STRIDED_DERIV: {
