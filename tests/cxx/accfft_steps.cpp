@@ -151,6 +151,46 @@ int main(int argc, char** argv) {
     fill(want, n, isize, istart, isize[2], [&](double x, double y, double z) { return s * s * F.f(x, y, z); });
     cudaMemcpy(back.data(), data2, cnt * sizeof(double), cudaMemcpyDeviceToHost);
     verdict("biharmonic (step5)", rel_l1(back.data(), want.data(), cnt), 1e-10);
+
+    // ---- the reference's other operator scheme (full 3-D transforms) and the inverse operators ----------------------
+    accfft_grad_gpu_slow_t<double, accfft_plan_gpu>(gx, gy, gz, data, plan, &XYZ, timer);
+    fill(want, n, isize, istart, isize[2], [&](double x, double y, double z) { return F.fy(x, y, z); });
+    cudaMemcpy(back.data(), gy, cnt * sizeof(double), cudaMemcpyDeviceToHost);
+    verdict("grad y, slow scheme (accfft_grad_gpu_slow_t)", rel_l1(back.data(), want.data(), cnt), 1e-10);
+    accfft_divergence_slow_gpu(data2, gx, gy, gz, plan, timer);
+    fill(want, n, isize, istart, isize[2], [&](double x, double y, double z) { return F.lap(x, y, z); });
+    cudaMemcpy(back.data(), data2, cnt * sizeof(double), cudaMemcpyDeviceToHost);
+    verdict("divergence, slow scheme", rel_l1(back.data(), want.data(), cnt), 1e-10);
+    accfft_inv_laplace_gpu(data2, data, plan, timer);          // f is a single mode: inv_laplace f = -f / |k|^2
+    fill(want, n, isize, istart, isize[2], [&](double x, double y, double z) { return -F.f(x, y, z) / s; });
+    cudaMemcpy(back.data(), data2, cnt * sizeof(double), cudaMemcpyDeviceToHost);
+    verdict("inverse laplace (GPU twin of accfft_inv_laplace)", rel_l1(back.data(), want.data(), cnt), 1e-10);
+    accfft_symbol_solve_gpu(data2, data, 1.0, 0.25, true, plan, timer);   // implicit heat step (1 + dt |k|^2)^-1, dt = 0.25
+    fill(want, n, isize, istart, isize[2], [&](double x, double y, double z) { return F.f(x, y, z) / (1.0 + 0.25 * s); });
+    cudaMemcpy(back.data(), data2, cnt * sizeof(double), cudaMemcpyDeviceToHost);
+    verdict("implicit heat step (accfft_symbol_solve_gpu)", rel_l1(back.data(), want.data(), cnt), 1e-10);
+
+    // ---- single-axis transforms (accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t): round trip = N_axis * f ------------------
+    {
+      const char* an[3] = {"x", "y", "z"};
+      for (int ax = 0; ax < 3; ++ax) {
+        if (ax == 0) {
+          accfft_execute_r2c_x_gpu_t<double, Complex>(plan, data, hat, timer);
+          accfft_execute_c2r_x_gpu_t<Complex, double>(plan, hat, data2, timer);
+        } else if (ax == 1) {
+          accfft_execute_r2c_y_gpu_t<double, Complex>(plan, data, hat, timer);
+          accfft_execute_c2r_y_gpu_t<Complex, double>(plan, hat, data2, timer);
+        } else {
+          accfft_execute_r2c_z_gpu_t<double, Complex>(plan, data, hat, timer);
+          accfft_execute_c2r_z_gpu_t<Complex, double>(plan, hat, data2, timer);
+        }
+        cudaMemcpy(back.data(), data2, cnt * sizeof(double), cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < cnt; ++i) back[i] /= n[ax];
+        char what[64];
+        snprintf(what, sizeof(what), "single-axis r2c_%s + c2r_%s round trip", an[ax], an[ax]);
+        verdict(what, rel_l1(back.data(), host.data(), cnt), 1e-10);
+      }
+    }
     accfft_destroy_plan_gpu(plan);
 
     // ---- step 2: in place (rows padded to 2 * (N2/2 + 1) reals) ----------------------------------------------------

@@ -60,6 +60,19 @@ def test_library_exports_the_reference_cxx_names(binaries):
         "accfft_laplace_gpuf(float*, float*, accfft_plan_gpuf*, double*)",
         "accfft_divergence_gpuf(float*, float*, float*, float*, accfft_plan_gpuf*, double*)",
         "accfft_biharmonic_gpuf(float*, float*, accfft_plan_gpuf*, double*)",
+        # single-axis executes and operator templates the reference's operators TU links against
+        "void accfft_execute_r2c_x_gpu_t<double, double [2]>(accfft_plan_gpu*, double*, double (*) [2], double*)",
+        "void accfft_execute_c2r_x_gpu_t<double [2], double>(accfft_plan_gpu*, double (*) [2], double*, double*)",
+        "void accfft_execute_r2c_y_gpu_t<double, double [2]>(accfft_plan_gpu*, double*, double (*) [2], double*)",
+        "void accfft_execute_c2r_y_gpu_t<double [2], double>(accfft_plan_gpu*, double (*) [2], double*, double*)",
+        "void accfft_execute_r2c_z_gpu_t<double, double [2]>(accfft_plan_gpu*, double*, double (*) [2], double*)",
+        "void accfft_execute_c2r_z_gpu_t<double [2], double>(accfft_plan_gpu*, double (*) [2], double*, double*)",
+        "void accfft_execute_r2c_y_gpu_t<float, float [2]>(accfft_plan_gpuf*, float*, float (*) [2], double*)",
+        "void accfft_grad_gpu_slow_t<double, accfft_plan_gpu>(double*, double*, double*, double*, accfft_plan_gpu*, std::bitset<3ul>*, double*)",
+        "accfft_divergence_slow_gpu(double*, double*, double*, double*, accfft_plan_gpu*, double*)",
+        # GPU twins of the reference's CPU-only inverse operators (extensions)
+        "accfft_inv_laplace_gpu(double*, double*, accfft_plan_gpu*, double*)",
+        "accfft_inv_biharmonic_gpu(double*, double*, accfft_plan_gpu*, double*)",
     ]
     missing = [w for w in wanted if w not in out]
     assert not missing, missing
