@@ -63,21 +63,35 @@ __global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_c2r(const 
 #ifndef ACCFFT_REAL_MINB
 #define ACCFFT_REAL_MINB 2   // two 512-thread CTAs per SM (<= 64 registers): measured 25 % faster than one (profiles/op_bench_r07.txt)
 #endif
-// real transforms along a strided axis (stage_real.cuh): same CTA shape as k_strided_c2c, a tile = 2*TC real columns
+// real transforms along a strided axis (stage_real.cuh): CTA shape of k_strided_c2c, a tile = 2*TC real columns.
+// ACCFFT_REAL_WIDE = 1 gives the lengths / precisions that have a wide shape (kernel_cfg.hpp: CfgW) that shape -- one shape
+// per kernel, chosen at compile time.  Measured on one GPU (512^3 single, 1024^3 single, 768^3 double): 3-25 % SLOWER than
+// the default shape for all three kernels (they are latency-, not segment-length-bound), hence off.
+#ifndef ACCFFT_REAL_WIDE
+#define ACCFFT_REAL_WIDE 0
+#endif
 template <class T, class S>
-__global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS, ACCFFT_REAL_MINB) k_strided_r2c(const __grid_constant__ StageDesc d) {
+struct RealCfg {
+  static constexpr bool WIDE = ACCFFT_REAL_WIDE != 0 && Cfg<T, S>::HAS_WIDE;
+  static constexpr int TC = WIDE ? CfgW<T, S>::TC : Cfg<T, S>::TC;
+  static constexpr int THREADS = WIDE ? CfgW<T, S>::STRIDED_THREADS : Cfg<T, S>::STRIDED_THREADS;
+  static constexpr int SMEM = WIDE ? CfgW<T, S>::STRIDED_SMEM : Cfg<T, S>::STRIDED_SMEM;
+  static constexpr int MINB = WIDE ? 1 : ACCFFT_REAL_MINB;
+};
+template <class T, class S>
+__global__ void __launch_bounds__(RealCfg<T, S>::THREADS, RealCfg<T, S>::MINB) k_strided_r2c(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  strided_r2c_body<T, S, Cfg<T, S>::TC>(d, ctx);
+  strided_r2c_body<T, S, RealCfg<T, S>::TC>(d, ctx);
 }
 template <class T, class S>
-__global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS, ACCFFT_REAL_MINB) k_strided_c2r(const __grid_constant__ StageDesc d) {
+__global__ void __launch_bounds__(RealCfg<T, S>::THREADS, RealCfg<T, S>::MINB) k_strided_c2r(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  strided_c2r_body<T, S, Cfg<T, S>::TC>(d, ctx);
+  strided_c2r_body<T, S, RealCfg<T, S>::TC>(d, ctx);
 }
 template <class T, class S>
-__global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS, ACCFFT_REAL_MINB) k_strided_deriv(const __grid_constant__ StageDesc d) {
+__global__ void __launch_bounds__(RealCfg<T, S>::THREADS, RealCfg<T, S>::MINB) k_strided_deriv(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  strided_deriv_body<T, S, Cfg<T, S>::TC>(d, ctx);
+  strided_deriv_body<T, S, RealCfg<T, S>::TC>(d, ctx);
 }
 
 template <class T, class S>
@@ -143,13 +157,14 @@ static int launch_one(const Launch& l, cudaStream_t st) {
   const long long npairs = ((long long)d.nA * d.nB + 1) / 2;
   return launch_kernel(k_contig_deriv<T, S>, (npairs + C::PC - 1) / C::PC, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
 #elif ACCFFT_KIND >= 5
-  const long long nb = (long long)d.nA * ((d.nB + 2 * C::TC - 1) / (2 * C::TC));
+  using RC = RealCfg<T, S>;
+  const long long nb = (long long)d.nA * ((d.nB + 2 * RC::TC - 1) / (2 * RC::TC));
 #if ACCFFT_KIND == 5
-  return launch_kernel(k_strided_r2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
+  return launch_kernel(k_strided_r2c<T, S>, nb, RC::THREADS, RC::SMEM, d, st, l.dry);
 #elif ACCFFT_KIND == 6
-  return launch_kernel(k_strided_c2r<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
+  return launch_kernel(k_strided_c2r<T, S>, nb, RC::THREADS, RC::SMEM, d, st, l.dry);
 #else
-  return launch_kernel(k_strided_deriv<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
+  return launch_kernel(k_strided_deriv<T, S>, nb, RC::THREADS, RC::SMEM, d, st, l.dry);
 #endif
 #elif ACCFFT_KIND == 1
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
