@@ -22,150 +22,21 @@
 
 using namespace accfft_b200;
 
-// ---------------------------------------------------------------------------------------------------
-// fiber CTA
-// ---------------------------------------------------------------------------------------------------
-struct CtaEmu {
-  int nthreads = 0;
-  std::vector<ucontext_t> ctx;
-  std::vector<char*> stacks;
-  std::vector<char> done;
-  ucontext_t sched;
-  int cur = 0;
-  std::function<void(int)> body;
-  static constexpr size_t kStack = 256 * 1024;
-  ~CtaEmu() {
-    for (char* s : stacks) free(s);
-  }
-};
-static thread_local CtaEmu* g_cta = nullptr;
+#include "emul_fiber.hpp"
 
-static void fiber_tramp() {
-  CtaEmu* c = g_cta;
-  const int tid = c->cur;
-  c->body(tid);
-  c->done[tid] = 1;
-  swapcontext(&c->ctx[tid], &c->sched);
-}
-static void fiber_sync() {
-  CtaEmu* c = g_cta;
-  const int tid = c->cur;
-  swapcontext(&c->ctx[tid], &c->sched);
-}
-static void run_cta(CtaEmu& c, int nthreads, std::function<void(int)> body) {
-  g_cta = &c;
-  c.body = body;
-  if ((int)c.stacks.size() < nthreads) {
-    for (int i = (int)c.stacks.size(); i < nthreads; ++i) c.stacks.push_back((char*)malloc(CtaEmu::kStack));
-  }
-  c.ctx.resize(nthreads);
-  c.done.assign(nthreads, 0);
-  c.nthreads = nthreads;
-  for (int i = 0; i < nthreads; ++i) {
-    getcontext(&c.ctx[i]);
-    c.ctx[i].uc_stack.ss_sp = c.stacks[i];
-    c.ctx[i].uc_stack.ss_size = CtaEmu::kStack;
-    c.ctx[i].uc_link = &c.sched;
-    makecontext(&c.ctx[i], fiber_tramp, 0);
-  }
-  bool alive = true;
-  while (alive) {
-    alive = false;
-    for (int i = 0; i < nthreads; ++i) {
-      if (c.done[i]) continue;
-      c.cur = i;
-      swapcontext(&c.sched, &c.ctx[i]);
-      if (!c.done[i]) alive = true;
-    }
-  }
-}
-
-struct EmuCtx {
-  int tid_;
-  long long bid_;
-  void* smem_;
-  int tid() const { return tid_; }
-  long long bid() const { return bid_; }
-  void* smem() const { return smem_; }
-  void sync() const { fiber_sync(); }
-  // bulk copies: same 16-byte rules as cp.async.bulk, enforced here so the emulator catches misuse
-  void bulk_fence() const {}
-  void bulk_store(void* gdst, const void* ssrc, unsigned bytes) const {
-    if (((uintptr_t)gdst | (uintptr_t)ssrc | bytes) & 15u) {
-      fprintf(stderr, "emul: misaligned bulk copy\n");
-      abort();
-    }
-    memcpy(gdst, ssrc, bytes);
-  }
-  void bulk_wait() const {}
-};
-
-template <class Body>
-static void run_grid(long long nblocks, int nthreads, size_t smem_bytes, Body body) {
-  CtaEmu cta;
-  std::vector<char> smem(smem_bytes + 64);
-  for (long long b = 0; b < nblocks; ++b) {
-    memset(smem.data(), 0xCD, smem.size());
-    run_cta(cta, nthreads, [&](int tid) {
-      EmuCtx ctx{tid, b, (void*)smem.data()};
-      body(ctx);
-    });
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// dispatch (same schedule table as the CUDA backend)
-// ---------------------------------------------------------------------------------------------------
-template <class T, class S>
-static void emu_launch_sched(const Launch& l) {
-  using C = Cfg<T, S>;
-  const StageDesc& d = l.desc;
-  switch (l.kind) {
-    case K_STRIDED_C2C: {
-      const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
-      run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) { strided_c2c_body<T, S, C::TC>(d, c); });
-      break;
-    }
-    case K_CONTIG_C2C: {
-      const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-      StageDesc ds = d;
-      ds.staged = (d.nseg > 1 && d.op == OP_NONE && d.accumulate == 0) ? 1 : 0;
-      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_STAGED_SMEM, [&](EmuCtx& c) { contig_c2c_body<T, S, C::PC>(ds, c); });
-      break;
-    }
-    case K_CONTIG_R2C: {
-      const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-      StageDesc ds = d;
-      ds.staged = (d.nseg > 1 && d.op == OP_NONE && d.accumulate == 0) ? 1 : 0;
-      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_STAGED_SMEM, [&](EmuCtx& c) { contig_r2c_body<T, S, C::PC>(ds, c); });
-      break;
-    }
-    case K_CONTIG_C2R: {
-      const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2r_body<T, S, C::PC>(d, c); });
-      break;
-    }
-    case K_CONTIG_DERIV: {
-      const long long npairs = ((long long)d.nA * d.nB + 1) / 2;
-      run_grid((npairs + C::PC - 1) / C::PC, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_deriv_body<T, S, C::PC>(d, c); });
-      break;
-    }
-    case K_STRIDED_R2C:
-    case K_STRIDED_C2R:
-    case K_STRIDED_DERIV: {
-      const long long nb = (long long)d.nA * ((d.nB + 2 * C::TC - 1) / (2 * C::TC));
-      run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) {
-        if (l.kind == K_STRIDED_R2C) strided_r2c_body<T, S, C::TC>(d, c);
-        else if (l.kind == K_STRIDED_C2R) strided_c2r_body<T, S, C::TC>(d, c);
-        else strided_deriv_body<T, S, C::TC>(d, c);
-      });
-      break;
-    }
-    default:
-      fprintf(stderr, "emul: unsupported kind %d\n", (int)l.kind);
-      abort();
-  }
-}
+// kernel-body instantiations live in emul_part.cpp (compiled EMU_NPARTS times, one slice of the schedule table each)
+#ifndef EMU_NPARTS
+#define EMU_NPARTS 8
+#endif
+bool emu_launch_part_0(const Launch&);
+bool emu_launch_part_1(const Launch&);
+bool emu_launch_part_2(const Launch&);
+bool emu_launch_part_3(const Launch&);
+bool emu_launch_part_4(const Launch&);
+bool emu_launch_part_5(const Launch&);
+bool emu_launch_part_6(const Launch&);
+bool emu_launch_part_7(const Launch&);
+static_assert(EMU_NPARTS == 8, "emul.cpp declares eight parts");
 
 static bool emu_supported(int N) {
 #define X(N_, G_, R0, R1, R2, R3) \
@@ -200,14 +71,9 @@ static void emu_launch(const Launch& l) {
     else emu_copy_stage<float>(l);
     return;
   }
-#define X(N_, G_, R0, R1, R2, R3)                                                       \
-  if (l.fftN == N_) {                                                                   \
-    if (l.prec == PREC_DOUBLE) emu_launch_sched<double, Sched<N_, G_, R0, R1, R2, R3>>(l); \
-    else emu_launch_sched<float, Sched<N_, G_, R0, R1, R2, R3>>(l);                        \
-    return;                                                                             \
-  }
-#include ACCFFT_SCHEDULES_FILE
-#undef X
+  if (emu_launch_part_0(l) || emu_launch_part_1(l) || emu_launch_part_2(l) || emu_launch_part_3(l) || emu_launch_part_4(l) ||
+      emu_launch_part_5(l) || emu_launch_part_6(l) || emu_launch_part_7(l))
+    return;
   fprintf(stderr, "emul: no schedule for N=%d\n", l.fftN);
   abort();
 }

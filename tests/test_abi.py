@@ -121,9 +121,9 @@ def test_create_comm_overwrites_bad_dims(nprocs, dims_in, dims_out):
 
 
 def test_supported_lengths():
-    for n in (2, 3, 4, 5, 6, 8, 12, 16, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 2048):
+    for n in (2, 3, 4, 5, 6, 8, 12, 16, 27, 64, 96, 125, 128, 192, 216, 250, 256, 384, 500, 512, 768, 1000, 1024, 1728, 2000, 2048):
         assert acc.length_supported(n), n
-    for n in (7, 11, 13, 1023):
+    for n in (7, 11, 13, 14, 81, 625, 1023, 4096):
         assert not acc.length_supported(n), n
 
 

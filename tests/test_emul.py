@@ -17,7 +17,7 @@ import emul_driver as emu  # noqa: E402
 
 CASES = [((8, 8, 8), (1, 1)), ((8, 8, 8), (2, 2)), ((12, 10, 16), (2, 4)), ((6, 12, 10), (3, 2)), ((5, 6, 6), (4, 2)),
          ((3, 5, 4), (4, 4)), ((32, 24, 20), (2, 2)), ((18, 30, 50), (1, 2)), ((45, 15, 90), (2, 1)), ((9, 10, 2), (1, 1)),
-         ((75, 4, 36), (1, 1))]
+         ((75, 4, 36), (1, 1)), ((27, 125, 54), (1, 1)), ((250, 6, 108), (2, 1)), ((4, 135, 250), (1, 2))]
 
 
 @pytest.fixture(scope="module", autouse=True)

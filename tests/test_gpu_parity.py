@@ -64,7 +64,9 @@ SIZES = [(8, 8, 8), (16, 12, 20), (2, 2, 2), (4, 6, 10), (5, 3, 8), (32, 48, 64)
          (128, 128, 128), (192, 160, 200), (24, 40, 768), (400, 20, 32), (12, 1024, 16), (2048, 8, 12),
          # N2 = 2048: the Z kernels run the 1024-point schedule (a different one in single precision, schedules.def);
          # 1024 / 768 / 1536 along Y and X: lengths that have a wide CTA shape in double
-         (4, 6, 2048), (1024, 12, 8), (8, 768, 12), (1536, 4, 6)]
+         (4, 6, 2048), (1024, 12, 8), (8, 768, 12), (1536, 4, 6),
+         # b, c = 3 families: decimal grids and 27-multiples (G up to 200 threads per column)
+         (125, 27, 250), (4, 6, 2000), (1000, 8, 12), (12, 1728, 8), (500, 6, 54), (8, 1500, 10), (6, 10, 1728), (216, 432, 108)]
 
 
 @pytest.mark.parametrize("n", SIZES)
@@ -251,7 +253,8 @@ def test_operators_against_oracle(cuda_device, n, single):
 
 @pytest.mark.parametrize("n,single", [((16, 20, 24), False), ((64, 64, 64), False), ((48, 40, 36), False), ((9, 15, 10), False),
                                       ((30, 6, 50), False), ((64, 64, 64), True), ((128, 96, 160), False), ((20, 18, 12), True),
-                                      ((1024, 4, 6), True), ((6, 1024, 8), True), ((4, 6, 1024), True), ((768, 6, 4), False)])
+                                      ((1024, 4, 6), True), ((6, 1024, 8), True), ((4, 6, 1024), True), ((768, 6, 4), False),
+                                      ((1000, 4, 6), False), ((6, 2000, 4), False), ((4, 6, 1000), True), ((125, 27, 54), False)])
 def test_single_axis_transforms_and_slow_operators(cuda_device, n, single):
     """accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t (src/accfft_gpu.cpp:1212-1604) against numpy's rfft along one axis, and the
     reference's two operator schemes (per-axis = default, full 3-D = *_slow) against the oracle and each other."""
