@@ -68,7 +68,10 @@ struct TmaCfg {
   }
   static constexpr int NST = nst();
   static constexpr int SMEM = NST * TILE_BYTES + XCH_BYTES + MISC_BYTES;
-  static constexpr bool OK = S::N >= 32 && ROW_BYTES % 16 == 0 && SMEM <= 220 * 1024;
+  // every box lands at  q * BOXR * ROW_BYTES  inside the tile: the TMA unit needs that offset 128-byte aligned
+  // (lengths whose largest divisor <= 256 is odd or only twice-even with narrow rows, e.g. 1500 with 32-byte rows, decline)
+  static constexpr bool OK = S::N >= 32 && ROW_BYTES % 16 == 0 && SMEM <= 220 * 1024 && (NBOX == 1 || (BOXR * ROW_BYTES) % 128 == 0) &&
+                             TILE_BYTES % 128 == 0;
 };
 
 // Stockham passes 1..NP-1 with the inter-pass exchange done through a buffer of REALS in two rounds (re, then im).

@@ -66,7 +66,8 @@ SIZES = [(8, 8, 8), (16, 12, 20), (2, 2, 2), (4, 6, 10), (5, 3, 8), (32, 48, 64)
          # 1024 / 768 / 1536 along Y and X: lengths that have a wide CTA shape in double
          (4, 6, 2048), (1024, 12, 8), (8, 768, 12), (1536, 4, 6),
          # b, c = 3 families: decimal grids and 27-multiples (G up to 200 threads per column)
-         (125, 27, 250), (4, 6, 2000), (1000, 8, 12), (12, 1728, 8), (500, 6, 54), (8, 1500, 10), (6, 10, 1728), (216, 432, 108)]
+         (125, 27, 250), (4, 6, 2000), (1000, 8, 12), (12, 1728, 8), (500, 6, 54), (8, 1500, 10), (6, 10, 1728), (216, 432, 108),
+         (135, 270, 6), (375, 4, 540), (8, 675, 750), (1080, 6, 4), (4, 1125, 6), (6, 4, 1350), (864, 4, 6), (450, 6, 4)]
 
 
 @pytest.mark.parametrize("n", SIZES)
