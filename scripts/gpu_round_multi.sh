@@ -10,6 +10,6 @@ for g in "$@"; do
   timeout 300 $RUN --master-port $p bench.py --gpus $N --steps 30 --warmup 5 --grid $g --no-e2e > gpurun_out/bench_${TAG}_n${N}_$g.json 2>> gpurun_out/bench_${TAG}_n$N.err
   p=$((p+1))
 done
-MGPU_QUICK=${MGPU_QUICK:-0} timeout 900 $RUN --master-port 29511 scripts/mgpu_check.py > gpurun_out/mgpu${N}_$TAG.log 2>&1
+MGPU_QUICK=${MGPU_QUICK:-0} timeout 900 $RUN --master-port 29511 tests/multi_gpu/mgpu_check.py > gpurun_out/mgpu${N}_$TAG.log 2>&1
 grep -h '"metric"' gpurun_out/bench_${TAG}_n$N*.json | cut -c1-400
 grep -v "^\*\|OMP_NUM\|^$" gpurun_out/mgpu${N}_$TAG.log | tail -70
