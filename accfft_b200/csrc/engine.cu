@@ -40,6 +40,9 @@ int accfft_launch_k7_p0(const Launch&, cudaStream_t);
 int accfft_launch_k7_p1(const Launch&, cudaStream_t);
 int accfft_launch_k8_p0(const Launch&, cudaStream_t);   // contiguous (Z-axis) derivative
 int accfft_launch_k8_p1(const Launch&, cudaStream_t);
+int accfft_has_wide_p0(int n);   // does the strided kernel have a wide CTA shape for this length? (k_tu.cu, kind 0)
+int accfft_has_wide_p1(int n);
+static bool has_wide(Prec p, int n) { return (p == PREC_DOUBLE ? accfft_has_wide_p0(n) : accfft_has_wide_p1(n)) != 0; }
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -344,8 +347,9 @@ int CudaBackend::launch(const Launch& l) {
       // and for single precision; the plain kernel wins on the plane-strided X passes in double).  Variant 3 = the plain
       // kernel in its wide CTA shape (kernel_cfg.hpp: CfgW).
       // Dry (plan-time) launches load BOTH; at run time the TMA kernel declines (-2) what it cannot take.
-      // Stages that store to peers are NVLink-bound and want as many storing threads as possible: plain kernel
-      // (profiles/mgpu8_r05.log: the one-CTA-per-SM TMA kernel lost 5-10 % there).
+      // Stages that store to peers are NVLink-bound and want as many storing threads and as long row segments as
+      // possible: never the one-CTA-per-SM TMA kernel (profiles/mgpu8_r05.log: it lost 5-10 % there), the wide shape where
+      // the length has one (profiles/mgpu8_r14.log), else the plain kernel.
       int v = l.variant ? l.variant : e->variant[l.slot >= 0 && l.slot < ACCFFTB_PROFILE_SLOTS ? l.slot : 6];
       // heuristic (ACCFFT_ESTIMATE, and every stage that stores to peers): peer stores want the longest row segments
       // the length allows -> wide shape where it exists (else it declines and the plain kernel runs)
@@ -353,6 +357,7 @@ int CudaBackend::launch(const Launch& l) {
       if (e->tma_mode == 0) v = 1;
       if (e->tma_mode == 2) v = 2;
       if (e->tma_mode == 3) v = 3;
+      if (v == 3 && !has_wide(l.prec, l.fftN)) v = 1;
       rc = -2;
       if (v == 2 || l.dry) rc = sel == 0 ? accfft_launch_k4_p0(l, e->stream) : accfft_launch_k4_p1(l, e->stream);
       if (rc == -2 || (l.dry && rc == 0)) {
@@ -500,7 +505,7 @@ static int autotune(Engine* e) {
     StageDesc& d = l.desc;
     if (d.nA <= 0 || d.nB <= 0) continue;
     if (d.nseg > 1) {   // stores to peers: NVLink-bound, not tunable on this rank alone -- see CudaBackend::launch
-      e->variant[l.slot] = 3;   // wide shape where the length has one, else the plain kernel
+      e->variant[l.slot] = has_wide(l.prec, l.fftN) ? 3 : 1;   // wide shape where the length has one, else the plain kernel
       continue;
     }
     // single local destination [a][k][b]: same bytes as the stage input, which fits one exchange buffer
@@ -527,6 +532,7 @@ static int autotune(Engine* e) {
       }
     }
     if (rc) break;
+    if (!has_wide(l.prec, l.fftN)) best[3] = 1e30f;   // that run fell back to the plain kernel
     e->variant[l.slot] = best[2] < best[1] ? (best[3] < best[2] ? 3 : 2) : (best[3] < best[1] ? 3 : 1);
   }
   cudaEventDestroy(a);

@@ -16,4 +16,11 @@ int ACCFFT_NAME(ACCFFT_KIND, ACCFFT_PREC)(const Launch& l, cudaStream_t st) { re
 #else
 int ACCFFT_NAME(ACCFFT_KIND, ACCFFT_PREC)(const Launch& l, cudaStream_t st) { return launch_any<float>(l, st); }
 #endif
+#if ACCFFT_KIND == 0
+#if ACCFFT_PREC == 0
+int accfft_has_wide_p0(int n) { return has_wide_any<double>(n); }
+#else
+int accfft_has_wide_p1(int n) { return has_wide_any<float>(n); }
+#endif
+#endif
 }  // namespace accfft_b200

@@ -179,6 +179,17 @@ static int launch_one(const Launch& l, cudaStream_t st) {
 }
 
 #endif
+#if ACCFFT_KIND == 0
+// does this length / precision have a wide CTA shape (kernel_cfg.hpp: CfgW)?  Host-side query for the variant choice.
+template <class T>
+static int has_wide_any(int n) {
+#define X(N_, G_, R0, R1, R2, R3) \
+  if (n == N_) return Cfg<T, Sched<N_, G_, R0, R1, R2, R3>>::HAS_WIDE ? 1 : 0;
+#include ACCFFT_SCHEDULES_FILE
+#undef X
+  return 0;
+}
+#endif
 #if ACCFFT_KIND == 4
 // ---- TMA-pipelined strided stage (stage_tma.cuh) ------------------------------------------------------------
 // returns -2 when the launch does not qualify (caller falls back to k_strided_c2c)
