@@ -100,6 +100,37 @@ def test_stage_sizes_match_oracle(n, dims):
                 assert list(start) == list(want[starts[which]]), (starts[which], rank)
 
 
+def test_sizes_match_oracle_on_a_seeded_random_sweep():
+    """300 random (grid, process grid) pairs, every rank: r2c / c2c size queries and all seven stage layouts of the C ABI
+    (64-bit decomposition in csrc/decomp.hpp) against the numpy restatement of src/accfft_common.cpp:49-256 -- uneven,
+    short and empty blocks included (more ranks than planes along an axis)."""
+    import random
+    rng = random.Random(20240607)
+    L = acc.lib()
+    i3 = lambda v: (ctypes.c_int * 3)(*v)
+    i2 = lambda v: (ctypes.c_int * 2)(*v)
+    names = ["osize_0", "osize_1", "osize_2", "osize_y", "osize_yi", "osize_x", "osize_xi"]
+    for _ in range(300):
+        n = tuple(rng.choice([1, 2, 3, 5, 6, 8, 12, 17, 30, 64, 100, 257]) for _ in range(3))
+        dims = (rng.choice([1, 2, 3, 4, 8]), rng.choice([1, 2, 3, 4, 8]))
+        nprocs = dims[0] * dims[1]
+        for rank in rng.sample(range(nprocs), min(nprocs, 4)):
+            comm = acc.Comm(rank, nprocs, dims)
+            for sizeof_real, r2c_fn, c2c_fn in ((8, acc.accfft_local_size_dft_r2c_gpu, acc.accfft_local_size_dft_c2c_gpu),
+                                                (4, acc.accfft_local_size_dft_r2c_gpuf, acc.accfft_local_size_dft_c2c_gpuf)):
+                got = r2c_fn(n, comm)
+                want = orc.local_size_dft_r2c(n, dims, comm.coords, sizeof_real)
+                assert got == (want["alloc_max"], want["isize"], want["istart"], want["osize"], want["ostart"]), (n, dims, rank)
+                got = c2c_fn(n, comm)
+                wc = orc.local_size_dft_c2c(n, dims, comm.coords, sizeof_real)
+                assert got == (wc["alloc_max"], wc["isize"], wc["istart"], wc["osize"], wc["ostart"]), (n, dims, rank)
+            want = orc.local_size_dft_r2c(n, dims, comm.coords, 8)
+            for which, name in enumerate(names):
+                size, start = i3((0,) * 3), i3((0,) * 3)
+                assert L.accfftb_stage_size(i3(n), i2(dims), i2(comm.coords), 0, 8, which, size, start) == 0
+                assert list(size) == list(want[name]), (n, dims, rank, name)
+
+
 def test_overflow_guard_returns_minus_one():
     # src/accfft_common.cpp:179-184: isize product > 2^31-1 -> -1
     comm = acc.Comm(0, 1, (1, 1))

@@ -178,6 +178,42 @@ def test_pipelined_slab_forward(n, np_, r2c, chunks, monkeypatch):
     w.close()
 
 
+def test_seeded_random_sweep_of_grids_and_process_grids():
+    """60 random small (grid, process grid) pairs through the emulated kernels and the real descriptor code: forward
+    spectrum, round trip, laplace, per-axis gradient and the single-axis transforms against the oracle.  Lengths are drawn
+    from the supported table, process grids up to 4 x 4 (so many ranks own short or empty pencils)."""
+    import random
+    rng = random.Random(1234)
+    small = [2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16, 18, 20, 24, 25, 27, 30]
+    for case in range(60):
+        n = (rng.choice(small), rng.choice(small), 2 * rng.choice([1, 2, 3, 4, 5, 6, 8, 9, 10, 12]))
+        np_ = (rng.choice([1, 2, 3, 4]), rng.choice([1, 2, 3, 4]))
+        x = orc.synthetic_real(n, 100 + case)
+        w = emu.World(n, np_, r2c=True)
+        X = orc.forward_r2c(x)
+        assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), X) < 1e-12, (n, np_)
+        assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, np_), x * x.size) < 1e-12, (n, np_)
+        if case % 3 == 0:
+            assert orc.rel_l2(orc.assemble_input(w.spectral(x, "laplace"), n, np_), orc.laplace(x)) < 1e-12, (n, np_)
+            g = emu.grad(w, x, fast=True)
+            for ax in range(3):
+                ref = orc.grad(x, ax)
+                got = orc.assemble_input(g[ax], n, np_)
+                den = max(float(np.linalg.norm(ref)), 1e-300)
+                assert float(np.linalg.norm(got - ref)) / den < 1e-12 or float(np.linalg.norm(got - ref)) < 1e-12, (n, np_, ax)
+            for axis in (0, 1, 2):
+                res = emu.axis_r2c(w, x, axis)
+                num = sum(float(np.sum(np.abs(a - b) ** 2)) for a, b in res)
+                den = sum(float(np.sum(np.abs(b) ** 2)) for a, b in res)
+                assert np.sqrt(num / den) < 1e-12, (n, np_, axis)
+        w.close()
+        if case % 4 == 0:
+            z = orc.synthetic_complex(n, 200 + case)
+            w = emu.World(n, np_, r2c=False)
+            assert orc.rel_l2(orc.assemble_output(w.forward(z), n, np_, r2c=False), orc.forward_c2c(z)) < 1e-12, (n, np_)
+            w.close()
+
+
 def test_unsupported_length_is_refused():
     with pytest.raises(RuntimeError):
         emu.World((7, 8, 8), (1, 1), r2c=True)
