@@ -18,6 +18,7 @@ extern "C" {
 typedef int MPI_Comm;
 typedef int MPI_Datatype;
 typedef int MPI_Op;
+typedef long long MPI_Offset;
 typedef struct { int MPI_SOURCE, MPI_TAG, MPI_ERROR; } MPI_Status;
 
 #define MPI_COMM_NULL (-1)

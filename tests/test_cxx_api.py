@@ -86,6 +86,23 @@ def test_mpi_shim_collectives(binaries, ranks):
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("n,ranks", [((12, 10, 14), 1), ((12, 10, 14), 4), ((5, 7, 6), 8), ((16, 3, 9), 2)])
+def test_npy_io_neighbour(binaries, tmp_path, n, ranks):
+    """write_npy / read_npy (include/accfft_utils.h): the .npy stand-in for the reference's read_pnetcdf / write_pnetcdf
+    (include/accfft_utils.h:24-38).  Ranks write their input pencils into ONE global file, read other pencils back, and numpy
+    sees the global C-order array.  CPU only (the shim runs without GPUs)."""
+    import numpy as np
+    exe = os.path.join(binaries, "npy_io_check")
+    path = str(tmp_path / "field.npy")
+    args = [path] + [str(v) for v in n]
+    cmd = [exe] + args if ranks == 1 else [MPIRUN, "-n", str(ranks), "--gpus-per-node", "0", exe] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+    a = np.load(path)
+    assert a.shape == tuple(n) and a.dtype == np.float64
+    assert np.array_equal(a.ravel(), np.arange(n[0] * n[1] * n[2], dtype=np.float64))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,ranks", [((64, 64, 64), 1), ((32, 48, 40), 1), ((64, 64, 64), 2), ((24, 20, 36), 2)])
 def test_acceptance_program_on_gpu(binaries, n, ranks):
