@@ -214,6 +214,29 @@ def test_seeded_random_sweep_of_grids_and_process_grids():
             w.close()
 
 
+def test_seeded_random_sweep_single_precision():
+    """the same sweep in single precision (tolerance 1e-5): 25 random grids / process grids, transforms, in-place layout,
+    per-axis divergence"""
+    import random
+    rng = random.Random(4321)
+    small = [2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16, 20, 24, 27, 30, 32]
+    for case in range(25):
+        n = (rng.choice(small), rng.choice(small), 2 * rng.choice([1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 16]))
+        np_ = (rng.choice([1, 2, 3, 4]), rng.choice([1, 2, 3, 4]))
+        x = orc.synthetic_real(n, 300 + case)
+        w = emu.World(n, np_, r2c=True, single=True)
+        X = orc.forward_r2c(x)
+        assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), X) < 1e-5, (n, np_)
+        assert orc.rel_l2(orc.assemble_output(w.forward(x, padded=True), n, np_), X) < 1e-5, (n, np_)
+        assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, np_), x * x.size) < 1e-5, (n, np_)
+        if case % 3 == 0:
+            a = [orc.synthetic_real(n, 400 + case + i) for i in range(3)]
+            ref = orc.divergence(*a)
+            got = orc.assemble_input(emu.divergence(w, *a, fast=True), n, np_)
+            assert float(np.linalg.norm(got - ref)) <= 2e-5 * max(float(np.linalg.norm(ref)), 1.0), (n, np_)
+        w.close()
+
+
 def test_unsupported_length_is_refused():
     with pytest.raises(RuntimeError):
         emu.World((7, 8, 8), (1, 1), r2c=True)
