@@ -28,7 +28,9 @@ trip < 1e-10, step5 closed-form grad/laplace/biharmonic < 1e-10) which ``tests/t
 replays against this module, (b) FFTW's own double-precision 1-D reference vectors that ship inside
 scipy (``scipy/fftpack/tests/fftw_double_ref.npz``), and (c) an O(N^2) long-double DFT written from
 the definition.  Forward-spectrum *values* remain "parity unpinned" in the strict sense that no
-reference-run output exists to compare with.
+reference-run output exists to compare with.  Independently of this module, the reference's own GPU
+step programs are compiled unmodified against the product (oracle/Makefile -> oracle/_ref/steps) and must print their
+own "Results are CORRECT!" verdict on the GPU (tests/test_reference_steps.py).
 """
 from __future__ import annotations
 
