@@ -13,6 +13,7 @@
 #include <unistd.h>
 #include <string>
 #include <vector>
+#include "mpi_shim_layout.hpp"
 
 int main(int argc, char** argv) {
   int n = 1, gpus = -1, i = 1;
@@ -27,7 +28,7 @@ int main(int argc, char** argv) {
   }
   if (gpus < 0) gpus = n;   // one GPU per rank by default
   const std::string name = "/accfft_mpi_" + std::to_string((long)getpid());
-  const size_t bytes = 64ull * 64 * 1024 + (1 << 20);   // >= sizeof(Shm) in mpi_shim.cpp
+  const size_t bytes = sizeof(accfft_mpi_shim::ShimShm);   // sparse: pages are committed on first touch
   const int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
   if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) {
     perror("accfft_mpirun: shared memory");

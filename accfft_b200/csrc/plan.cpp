@@ -504,6 +504,7 @@ int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spe
     xi.desc.opAxis = ax;
     xi.desc.scale = 1.0;
     xi.desc.opOnLoad = 1;
+    xi.desc.opFullAxis = 1;
     if (!empty(xi) && (rc = be->launch(xi))) return rc;
     if (nprocs > 1 && (rc = be->barrier())) return rc;
     Launch yi = inv_y();
@@ -529,6 +530,7 @@ int Plan::execute_divergence(const void* const ins[3], void* out, void* spec) {
     x.desc.op = OP_GRAD;
     x.desc.opAxis = ax;
     x.desc.scale = inv_n;
+    x.desc.opFullAxis = 1;
     x.desc.accumulate = ax > 0;
     if (!empty(x) && (rc = be->launch(x))) return rc;
   }

@@ -34,7 +34,8 @@ enum SpectralOp : int {
   // include/accfft_operators.h:57-60, src/operators.txx:275-392) or as user kernels between two transforms
   // (steps/step4/kernels.cu:22-112 Poisson filter, steps/step6 heat step); here they ride on the X stage like the others.
   OP_INV_LAPLACE = 5,     // scale / -(|k|^2), 0 where |k|^2 == 0      (src/operators.txx:318-327)
-  OP_INV_BIHARMONIC = 6,  // scale / |k|^4,    0 where |k|^2 == 0      (src/operators.txx:377-386)
+  OP_INV_BIHARMONIC = 6,  // scale / |k|^4 with the PLAIN wave numbers (the reference has the Nyquist rule commented out here,
+                          // src/operators.txx:362-375) and the zero mode passed through (`if (wave == 0) wave = 1`, :379-381)
   OP_SYMBOL_LIN = 7,      // scale * (opA + opB |k|^2)                  (explicit heat step: 1 - dt |k|^2)
   OP_SYMBOL_INV = 8,      // scale / (opA + opB |k|^2), 0 where the denominator is 0   (Helmholtz / implicit heat / Poisson)
 };
@@ -63,6 +64,9 @@ struct StageDesc {
                          // in a destination whose rows this rank enters at an unaligned offset (inverse Y stage)
   int inv;               // 1: inverse transform (sign +1), done as swap(re,im) . forward . swap(re,im)
   double opA, opB;       // OP_SYMBOL_LIN / OP_SYMBOL_INV coefficients
+  int opFullAxis;        // OP_GRAD on an axis that the 3-D transform treats as a full COMPLEX axis (the reference's "slow" 3-D scheme,
+                         // src/operators_cuda.cu:34-37): only X == N/2 is zeroed.  0 = the per-axis real-transform scheme, where
+                         // the mode pair +-floor(N/2) vanishes as a pair (differs for odd N only).
   int staged;            // contiguous kernels with nseg > 1: outputs are collected in shared memory per destination
                          // segment and leave the CTA as bulk (TMA) copies of whole runs -- full 128-byte lines on the
                          // NVLink wire instead of one partial-line packet per warp store.  Set by the launcher.
@@ -111,19 +115,27 @@ ACC_HD cplx<T> apply_op(const StageDesc& d, cplx<T> v, int k, int a, int b) {
     // On a full (c2c) axis that means X == N/2 and X == N - N/2 (the same index when N is even).
     const int ax = d.opAxis;
     const int X = freq_index(d, ax, k, a, b), N = d.n[ax];
-    const double w = (X == N - N / 2) ? 0.0 : d.scale * (double)wave_number(X, N);
+    const double w = (X == N - N / 2 && !d.opFullAxis) ? 0.0 : d.scale * (double)wave_number(X, N);
     return {T(-w * v.y), T(w * v.x)};
   }
-  const long long wx = wave_number(freq_index(d, 0, k, a, b), d.n[0]);
-  const long long wy = wave_number(freq_index(d, 1, k, a, b), d.n[1]);
-  const long long wz = wave_number(freq_index(d, 2, k, a, b), d.n[2]);
+  long long wx, wy, wz;
+  if (d.op == OP_INV_BIHARMONIC) {   // plain signed wave numbers: X == N/2 keeps N/2
+    const int X = freq_index(d, 0, k, a, b), Y = freq_index(d, 1, k, a, b), Z = freq_index(d, 2, k, a, b);
+    wx = X > d.n[0] / 2 ? X - d.n[0] : X;
+    wy = Y > d.n[1] / 2 ? Y - d.n[1] : Y;
+    wz = Z > d.n[2] / 2 ? Z - d.n[2] : Z;
+  } else {
+    wx = wave_number(freq_index(d, 0, k, a, b), d.n[0]);
+    wy = wave_number(freq_index(d, 1, k, a, b), d.n[1]);
+    wz = wave_number(freq_index(d, 2, k, a, b), d.n[2]);
+  }
   const double s2 = (double)(wx * wx + wy * wy + wz * wz);
   double w;
   switch (d.op) {
     case OP_LAPLACE: w = -s2; break;
     case OP_BIHARMONIC: w = s2 * s2; break;
     case OP_INV_LAPLACE: w = s2 == 0.0 ? 0.0 : -1.0 / s2; break;
-    case OP_INV_BIHARMONIC: w = s2 == 0.0 ? 0.0 : 1.0 / (s2 * s2); break;
+    case OP_INV_BIHARMONIC: w = s2 == 0.0 ? 1.0 : 1.0 / (s2 * s2); break;
     case OP_SYMBOL_LIN: w = d.opA + d.opB * s2; break;
     default: {
       const double den = d.opA + d.opB * s2;

@@ -105,12 +105,24 @@ def cpu_roundtrip(n, workers, x=None):
     return t
 
 
+THREAD_ENV = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS", "DUCC0_NUM_THREADS",
+              "VECLIB_MAXIMUM_THREADS", "OMP_THREAD_LIMIT")
+
+
 def run_reference(args):
-    from oracle import accfft_oracle as orc
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which pins scipy's FFT thread pool to ONE thread
+    # (round 1: 13.9 GFLOP/s under torchrun vs 179 stand-alone on the same box).  The reference arm is "all the host
+    # threads it can use": drop every thread cap BEFORE numpy / scipy are imported.
+    capped = {k: os.environ.pop(k) for k in THREAD_ENV if k in os.environ}
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))   # and undo any inherited CPU pinning
+    except Exception:
+        pass
+    from oracle import accfft_oracle as orc
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     n_full = (args.n, args.n, args.n)
     n_small = (min(256, args.n),) * 3
     cpu_roundtrip((64, 64, 64), cores)                      # spin up the pocketfft thread pool
@@ -127,15 +139,23 @@ def run_reference(args):
     x = orc.cpu_input(n)
     for _ in range(args.warmup):
         cpu_roundtrip(n, cores, x)
+    c0, w0 = time.process_time(), time.perf_counter()
     dt = sum(cpu_roundtrip(n, cores, x) for _ in range(args.steps)) / max(args.steps, 1)
+    busy = (time.process_time() - c0) / max(time.perf_counter() - w0, 1e-9)   # CPU seconds per wall second = threads kept busy
     gf = 2 * flops_per_transform(n) / dt / 1e9
-    sample = "%d^3 double r2c+c2r round trip per step (scipy.fft pocketfft, workers=%d)" % (n[0], cores)
+    sample = "%d^3 double r2c+c2r round trip per step (scipy.fft pocketfft, workers=%d, %.1f threads busy on average)" % (
+        n[0], cores, busy)
+    if cores > 2 and busy < 1.5 and n[0] >= 256:   # (tiny grids do not keep a thread pool busy)
+        raise SystemExit("reference arm ran on %.1f threads of %d: a thread cap is still in force (%r)" % (busy, cores, capped))
     line = {
         "impl": "reference", "metric": METRIC, "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%d^3 double r2c+c2r round trip" % args.n, "sample": sample,
-                   "note": "CPU oracle port; the reference's FFTW+MPI path cannot be built here (no MPI, no FFTW)"},
+        "config": {"workload": "%d^3 double r2c+c2r round trip (forward + inverse = 1 step)" % n[0], "sample": sample,
+                   "requested": "%d^3" % args.n, "thread_caps_removed": capped, "threads_busy": busy,
+                   "note": "CPU oracle port (scipy pocketfft): the stand-in for FFTW+MPI, which cannot be built here (no MPI, "
+                           "no FFTW); oracle/_ref holds the reference's own decomposition / transpose / operator code built "
+                           "against a definitional-DFT fftw3.h shim -- a parity pin, not a timing baseline"},
         "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -382,6 +382,23 @@ def grad(x: np.ndarray, axis: int) -> np.ndarray:
     return np.fft.ifft(X, axis=axis).real
 
 
+def grad_slow(x: np.ndarray, axis: int) -> np.ndarray:
+    """accfft_grad_slow_t component (src/operators.txx / src/operators_gpu.txx:72-170): full 3-D r2c, multiply by
+    i k_axis / N with ONLY X == N/2 zeroed (src/operators_cuda.cu:34-37), full 3-D c2r.  Identical to grad() for even
+    N; for odd N along x or y the mirror mode N - N/2 survives here (the fast scheme's real transform drops the pair)."""
+    n = x.shape
+    shape = [1, 1, 1]
+    shape[axis] = n[axis] if axis < 2 else n[2] // 2 + 1
+    k = wave_numbers(n[axis], shape[axis]).reshape(shape)
+    X = forward_r2c(x) * (1j * k)
+    return inverse_c2r(X, n) / (n[0] * n[1] * n[2])
+
+
+def divergence_slow(ax: np.ndarray, ay: np.ndarray, az: np.ndarray) -> np.ndarray:
+    """accfft_divergence_slow_t: sum of the three grad_slow-style derivatives (one inverse transform of the summed spectra)."""
+    return grad_slow(ax, 0) + grad_slow(ay, 1) + grad_slow(az, 2)
+
+
 def laplace(x: np.ndarray) -> np.ndarray:
     n = x.shape
     kx, ky, kz = _khat(n)
@@ -412,11 +429,25 @@ def inv_laplace(x: np.ndarray) -> np.ndarray:
     return np.fft.irfftn(np.fft.rfftn(np.asarray(x, np.float64)) * w, s=n, axes=(0, 1, 2))
 
 
+def _k2_plain(n):
+    """|k|^2 with the plain signed wave numbers (X > N/2 -> X - N; X == N/2 stays N/2): the reference's inv_biharmonic has
+    the Nyquist rule commented out (src/operators.txx:362-375)."""
+    def k(N, count=None):
+        X = np.arange(N if count is None else count)
+        return np.where(X > N // 2, X - N, X).astype(np.float64)
+    kx = k(n[0])[:, None, None]
+    ky = k(n[1])[None, :, None]
+    kz = k(n[2], n[2] // 2 + 1)[None, None, :]
+    return kx * kx + ky * ky + kz * kz
+
+
 def inv_biharmonic(x: np.ndarray) -> np.ndarray:
-    """accfft_inv_biharmonic: F^-1[F[x] / |k|^4], 0 where |k|^2 == 0  (src/operators.txx:335-392)."""
+    """accfft_inv_biharmonic (src/operators.txx:335-392), as the reference computes it (pinned by tests/golden/ref_*.npz):
+    F^-1[F[x] / |k|^4] with the PLAIN wave numbers (no Nyquist zeroing, :362-375) and the zero mode passed through
+    unchanged (`if (wave == 0) wave = 1`, :379-381) -- unlike accfft_inv_laplace, which zeroes both."""
     n = x.shape
-    k2 = _k2(n)
-    w = np.zeros_like(k2)
+    k2 = _k2_plain(n)
+    w = np.ones_like(k2)
     np.divide(1.0, k2 * k2, out=w, where=k2 != 0)
     return np.fft.irfftn(np.fft.rfftn(np.asarray(x, np.float64)) * w, s=n, axes=(0, 1, 2))
 
@@ -560,3 +591,18 @@ def cpu_roundtrip_seconds(n, dtype=np.float64, repeats=1, workers=None, c2c=Fals
         best = min(best, time.perf_counter() - t0)
     del y
     return best, workers
+
+
+def hashed_field(n, seed: int, c2c=False) -> np.ndarray:
+    """Seeded test field that C++ can regenerate bit for bit (oracle/ref_driver.cpp: hashed()): splitmix64 of
+    (seed, linear global index) mapped to [-1, 1).  Complex fields interleave re / im at indices 2g, 2g+1."""
+    total = int(np.prod(n)) * (2 if c2c else 1)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.arange(total, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    v = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0) * 2.0 - 1.0
+    if c2c:
+        return (v[0::2] + 1j * v[1::2]).reshape(tuple(n))
+    return v.reshape(tuple(n))

@@ -50,15 +50,16 @@ def test_c2c_all_ranks(n, np_):
 @pytest.mark.parametrize("n,np_", [((8, 8, 8), (1, 1)), ((12, 10, 16), (2, 2)), ((5, 6, 6), (2, 1)), ((9, 5, 10), (1, 2)),
                                    ((6, 12, 10), (3, 2))])
 def test_grad_divergence_all_ranks(n, np_):
-    # odd lengths included: the +-floor(N/2) mode pair is zeroed as a pair, like the reference's per-axis r2c scheme
+    # odd lengths included: the full-3-D ("slow") scheme zeroes only X == N/2 (src/operators_cuda.cu:34-37), pinned by
+    # tests/golden/ref_*.npz; the per-axis scheme (test_grad_per_axis_*) drops the +-floor(N/2) pair
     x = orc.synthetic_real(n, 17)
     w = emu.World(n, np_, r2c=True)
     g = emu.grad(w, x)
     for ax in range(3):
-        assert orc.rel_l2(orc.assemble_input(g[ax], n, np_), orc.grad(x, ax)) < 1e-12, ax
+        assert orc.rel_l2(orc.assemble_input(g[ax], n, np_), orc.grad_slow(x, ax)) < 1e-12, ax
     a = [orc.synthetic_real(n, 20 + i) for i in range(3)]
     dv = emu.divergence(w, *a)
-    assert orc.rel_l2(orc.assemble_input(dv, n, np_), orc.divergence(*a)) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(dv, n, np_), orc.divergence_slow(*a)) < 1e-12
     assert orc.rel_l2(orc.assemble_input(w.spectral(x, "biharmonic"), n, np_), orc.biharmonic(x)) < 1e-12
     w.close()
 
