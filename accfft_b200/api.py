@@ -77,6 +77,10 @@ def lib():
     L.accfftb_plan_alloc_max.argtypes = [c_vp]
     L.accfftb_plan_launch_count.restype = c_ll
     L.accfftb_plan_launch_count.argtypes = [c_vp]
+    L.accfftb_plan_copy_count.restype = c_ll
+    L.accfftb_plan_copy_count.argtypes = [c_vp]
+    L.accfftb_plan_exchange_mode.argtypes = [c_vp, ip, ip]
+    L.accfftb_plan_check.argtypes = [c_vp]
     L.accfftb_plan_destroy.argtypes = [c_vp]
     L.accfftb_execute_r2c.argtypes = [c_vp, c_vp, c_vp, c_dp, c_int]
     L.accfftb_execute_c2r.argtypes = [c_vp, c_vp, c_vp, c_dp, c_int]
@@ -240,7 +244,7 @@ class Plan:
     def set_profiling(self, on: bool):
         _check(lib().accfftb_plan_set_profiling(self._h, int(on)), "set_profiling")
 
-    PROFILE_SLOTS = ("fwd_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "inv_z", "barrier", "axis_copy", "axis_fft")
+    PROFILE_SLOTS = ("fwd_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "inv_z", "barrier", "axis_copy", "axis_fft", "ce_copy")
 
     def profile_read(self):
         """-> {slot name: (total ms, launches)} since the last read (synchronises the plan's stream)"""
@@ -257,6 +261,22 @@ class Plan:
     @property
     def launch_count(self) -> int:
         return int(lib().accfftb_plan_launch_count(self._h))
+
+    @property
+    def copy_count(self) -> int:
+        """copy-engine transfers enqueued so far (slab-grid exchange)"""
+        return int(lib().accfftb_plan_copy_count(self._h))
+
+    def exchange_mode(self):
+        """-> {"mode": "copy_engine" | "peer_store" | "local", "chunks": n, "lanes": n}"""
+        ch, ln = ctypes.c_int(0), ctypes.c_int(0)
+        m = lib().accfftb_plan_exchange_mode(self._h, ctypes.byref(ch), ctypes.byref(ln))
+        mode = "copy_engine" if m == 1 else ("peer_store" if self.comm.nprocs > 1 else "local")
+        return {"mode": mode, "chunks": ch.value, "lanes": ln.value}
+
+    def check(self):
+        """accfftb_plan_check: raises once an inter-GPU barrier of the plan has timed out (sticky); never synchronises"""
+        _check(lib().accfftb_plan_check(self._h), "accfftb_plan_check")
 
     # ---- transforms ----------------------------------------------------------------------------
     @staticmethod

@@ -78,7 +78,7 @@ struct BarrierDesc {
   int rank, nprocs;
   unsigned long long epoch;
   long long timeout_cycles;
-  int* status;   // device word, set to 1 on timeout
+  int* status;   // host-mapped word, set to 1 on timeout: sticky, read by the host without synchronising (engine_check)
 };
 
 __global__ void __launch_bounds__(32) k_barrier(const __grid_constant__ BarrierDesc b) {
@@ -89,7 +89,11 @@ __global__ void __launch_bounds__(32) k_barrier(const __grid_constant__ BarrierD
     unsigned long long* remote = b.flags[q] + b.rank;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(b.epoch) : "memory");
   }
-  for (int q = (int)threadIdx.x; q < b.nprocs; q += 32) {
+  // A barrier that timed out leaves the plan dead: the status word is sticky, every later barrier of the plan returns at
+  // once (this rank still signalled above, so that healthy peers are not dragged into the time-out as well) and every
+  // later API call fails with ACCFFTB_ERR_TIMEOUT before it launches anything (engine_check).
+  const bool dead = *(volatile int*)b.status != 0;
+  for (int q = (int)threadIdx.x; q < b.nprocs && !dead; q += 32) {
     const unsigned long long* mine = b.flags[b.rank] + q;
     const long long t0 = clock64();
     unsigned spins = 0;
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(32) k_barrier(const __grid_constant__ BarrierD
       if (v >= b.epoch) break;
       if (++spins > 64) {   // peers normally arrive within a few microseconds: spin first, back off later
         if (clock64() - t0 > b.timeout_cycles) {
-          *b.status = 1;
+          *(volatile int*)b.status = 1;
           break;
         }
         __nanosleep(64);
@@ -159,7 +163,14 @@ struct CudaBackend : Backend {
   int hand(int from) override;
   int join() override;
   int barrier_on(int lane) override;
-  int link(cudaStream_t from, cudaStream_t to);
+  int link_streams(cudaStream_t from, cudaStream_t to);
+  // copy-engine exchange (plan.hpp)
+  int ce_chunks() override;
+  int copy_lanes() override;
+  void* staging() override;
+  int link(int from, int to) override;
+  int copy2d(int lane, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) override;
+  int local_variant(const Launch& l) override;
 };
 
 constexpr size_t kFlagBytes = 4096;
@@ -174,6 +185,16 @@ struct Engine {
   bool blocking = true;
   cudaStream_t aux = nullptr;  // lane 1 of software-pipelined stages (lowest priority: its kernels wait on NVLink anyway)
   int overlap_chunks = 1;      // ACCFFT_B200_OVERLAP: chunks of the pipelined Z/Y stages on slab grids (<= 1: off)
+  // copy-engine exchange on slab grids (Plan::forward_slab_ce / inverse_slab_ce)
+  static constexpr int kMaxCopyLanes = 8;
+  int ce_chunks = 0;           // ACCFFT_B200_CE: chunks per exchanging stage (0: direct peer stores instead)
+  int ce_lanes = 0;            // ACCFFT_B200_CE_LANES: copy streams (copies to different peers overlap)
+  cudaStream_t copy_streams[kMaxCopyLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  char* stage_buf = nullptr;   // local staging buffer of the exchanging stage (one exchange buffer long)
+  int variant_local[ACCFFTB_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // tuned kernel variant of a stage when it stores locally
+  int* status_h = nullptr;     // host view of the barrier time-out word (mapped pinned memory)
+  long long timeout_cycles = 20LL * 1000 * 1000 * 1000;
+  cudaStream_t lane_stream(int lane) const { return lane <= 0 ? stream : (lane <= kMaxCopyLanes && copy_streams[lane - 1] ? copy_streams[lane - 1] : aux); }
   std::vector<cudaEvent_t> sync_events;   // ring of timing-less events for fork / hand / join
   size_t sync_next = 0;
   int tma_mode = 1;            // ACCFFT_B200_TMA: 0 = plain kernel only, 1 = tuned / heuristic, 2 = TMA kernel always, 3 = wide shape always
@@ -186,7 +207,8 @@ struct Engine {
   std::vector<unsigned long long*> flag_ptrs;
   unsigned long long epoch = 0;
   long long launches = 0;
-  int variant[ACCFFTB_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per stage slot: 0 heuristic, 1 plain, 2 TMA (set by autotune)
+  long long copies = 0;        // copy-engine transfers enqueued (not kernels: counted apart from `launches`)
+  int variant[ACCFFTB_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // per stage slot: 0 heuristic, 1 plain, 2 TMA (set by autotune)
   std::map<std::pair<int, int>, void*> tables;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   // timing of the current call
@@ -279,16 +301,20 @@ struct LaneScope {
   Engine* e;
   cudaStream_t saved;
   LaneScope(Engine* e_, int lane) : e(e_), saved(e_->stream) {
-    if (lane == 1 && e->aux) e->stream = e->aux;
+    if (lane >= 1) {
+      cudaStream_t s = e->lane_stream(lane);
+      if (s) e->stream = s;
+    }
   }
   ~LaneScope() { e->stream = saved; }
 };
 
 int CudaBackend::pipeline_chunks() { return (e->timing || !e->aux) ? 1 : e->overlap_chunks; }
 
-int CudaBackend::link(cudaStream_t from, cudaStream_t to) {
+int CudaBackend::link_streams(cudaStream_t from, cudaStream_t to) {
+  if (from == to) return 0;
   if (e->sync_events.empty()) {
-    e->sync_events.resize(64, nullptr);
+    e->sync_events.resize(256, nullptr);
     for (auto& ev : e->sync_events) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
   cudaEvent_t ev = e->sync_events[e->sync_next++ % e->sync_events.size()];
@@ -296,9 +322,31 @@ int CudaBackend::link(cudaStream_t from, cudaStream_t to) {
   CU(cudaStreamWaitEvent(to, ev, 0));
   return 0;
 }
-int CudaBackend::fork() { return link(e->stream, e->aux); }
-int CudaBackend::hand(int from) { return from == 0 ? link(e->stream, e->aux) : link(e->aux, e->stream); }
-int CudaBackend::join() { return link(e->aux, e->stream); }
+int CudaBackend::fork() { return link_streams(e->stream, e->aux); }
+int CudaBackend::hand(int from) { return from == 0 ? link_streams(e->stream, e->aux) : link_streams(e->aux, e->stream); }
+int CudaBackend::join() { return link_streams(e->aux, e->stream); }
+
+// ---- copy-engine exchange ---------------------------------------------------------------------------------------
+int CudaBackend::ce_chunks() { return (e->timing || !e->stage_buf || e->ce_lanes < 1) ? 0 : e->ce_chunks; }
+int CudaBackend::copy_lanes() { return e->ce_lanes; }
+void* CudaBackend::staging() { return e->stage_buf; }
+int CudaBackend::link(int from, int to) { return link_streams(e->lane_stream(from), e->lane_stream(to)); }
+int CudaBackend::local_variant(const Launch& l) {
+  const int v = e->variant_local[l.slot >= 0 && l.slot < ACCFFTB_PROFILE_SLOTS ? l.slot : 6];
+  if (v) return v;
+  // heuristic of CudaBackend::launch for a LOCAL stage (the launch itself sees nseg > 1 and would pick the peer-store shape)
+  return (l.desc.nA > 1 || l.prec == PREC_FLOAT) ? 2 : 1;
+}
+int CudaBackend::copy2d(int lane, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) {
+  if (lane < 1 || lane > e->ce_lanes) return fail(ACCFFTB_ERR_STATE, "copy lane out of range");
+  if (!width || !height) return 0;
+  LaneScope lane_scope(e, lane);
+  ScopedProfile pf(e, 9);
+  if (height == 1) CU(cudaMemcpyAsync(dst, src, width, cudaMemcpyDeviceToDevice, e->stream));
+  else CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToDevice, e->stream));
+  e->copies++;
+  return 0;
+}
 int CudaBackend::barrier_on(int lane) {
   LaneScope ls(e, lane);
   return barrier();
@@ -403,7 +451,7 @@ int CudaBackend::barrier() {
   b.rank = e->rank;
   b.nprocs = e->plan.nprocs;
   b.epoch = ++e->epoch;
-  b.timeout_cycles = 20LL * 1000 * 1000 * 1000;   // ~10 s at 2 GHz: a peer died or diverged
+  b.timeout_cycles = e->timeout_cycles;   // 10 s of SM clock (cudaDevAttrClockRate): a peer died or diverged
   b.status = e->status_d;
   k_barrier<<<1, 32, 0, e->stream>>>(b);
   cudaError_t err = cudaGetLastError();
@@ -412,16 +460,21 @@ int CudaBackend::barrier() {
   return 0;
 }
 
+// The barrier time-out word lives in mapped pinned host memory: the host reads it without synchronising anything.  It is
+// sticky -- once a barrier of this plan has timed out the stages after it ran on incomplete peer data, so every later call on
+// the plan fails before launching (blocking or not); non-blocking callers can also poll accfftb_plan_check().
+static int engine_check(Engine* e) {
+  if (e->status_h && *(volatile int*)e->status_h)
+    return fail(ACCFFTB_ERR_TIMEOUT, "an inter-GPU barrier of this plan timed out (a peer died or diverged): results since then are "
+                                     "invalid and the plan is unusable; destroy it");
+  return 0;
+}
+
 static int engine_finish(Engine* e, int rc) {
   if (rc) return rc;
   if (e->blocking) {
     CU(cudaStreamSynchronize(e->stream));
-    if (e->plan.nprocs > 1) {
-      int st = 0;
-      CU(cudaMemcpyAsync(&st, e->status_d, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-      CU(cudaStreamSynchronize(e->stream));
-      if (st) return fail(ACCFFTB_ERR_TIMEOUT, "inter-GPU barrier timed out");
-    }
+    return engine_check(e);
   }
   return 0;
 }
@@ -437,7 +490,10 @@ static void engine_free(Engine* e) {
   for (auto& kv : e->tables) cudaFree(kv.second);
   if (e->slab) cudaFree(e->slab);
   if (e->spec) cudaFree(e->spec);
-  if (e->status_d) cudaFree(e->status_d);
+  if (e->status_h) cudaFreeHost(e->status_h);
+  if (e->stage_buf) cudaFree(e->stage_buf);
+  for (auto& cs : e->copy_streams)
+    if (cs) cudaStreamSynchronize(cs), cudaStreamDestroy(cs);
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
   if (e->ev[1]) cudaEventDestroy(e->ev[1]);
   for (auto& r : e->recs) cudaEventDestroy(r.a), cudaEventDestroy(r.b);
@@ -658,8 +714,17 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
   // spectrum scratch of the operators: allocated now, never inside a collective call (cudaMalloc synchronises
   // the device, which must not happen while a peer's barrier kernel waits for this rank)
   if (err == cudaSuccess && kind == ACCFFTB_R2C) err = cudaMalloc(&e->spec, e->bufsz);
-  if (err == cudaSuccess) err = cudaMalloc((void**)&e->status_d, sizeof(int));
-  if (err == cudaSuccess) err = cudaMemset(e->status_d, 0, sizeof(int));
+  if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->status_h, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable);
+  if (err == cudaSuccess) {
+    *e->status_h = 0;
+    err = cudaHostGetDevicePointer((void**)&e->status_d, e->status_h, 0);
+  }
+  if (err == cudaSuccess) {
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device) == cudaSuccess && khz > 0)
+      e->timeout_cycles = 10LL * 1000 * (long long)khz;   // 10 seconds of SM clock
+    if (const char* m = getenv("ACCFFT_B200_BARRIER_TIMEOUT_MS")) e->timeout_cycles = (long long)atoll(m) * (long long)(khz > 0 ? khz : 2000000);
+  }
   if (err == cudaSuccess) err = cudaEventCreate(&e->ev[0]);
   if (err == cudaSuccess) err = cudaEventCreate(&e->ev[1]);
   if (err == cudaSuccess) err = cudaDeviceSynchronize();
@@ -681,6 +746,23 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
       int lo = 0, hi = 0;
       cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least priority (numerically greatest)
       if (cudaStreamCreateWithPriority(&e->aux, cudaStreamNonBlocking, lo) != cudaSuccess) e->aux = nullptr, cudaGetLastError();
+    }
+    // copy-engine exchange: slab grids only (one exchange per transform, both of its ends local)
+    if (pl.nprocs > 1 && c_dims[1] == 1) {
+      e->ce_chunks = 4;
+      e->ce_lanes = std::min(pl.nprocs - 1, 4);
+      if (const char* m = getenv("ACCFFT_B200_CE")) e->ce_chunks = atoi(m);
+      if (const char* m = getenv("ACCFFT_B200_CE_LANES")) e->ce_lanes = std::max(1, std::min(atoi(m), (int)Engine::kMaxCopyLanes));
+      if (e->ce_chunks > 0) {
+        cudaError_t ce = cudaMalloc((void**)&e->stage_buf, e->bufsz);
+        for (int l = 0; l < e->ce_lanes && ce == cudaSuccess; ++l)
+          ce = cudaStreamCreateWithFlags(&e->copy_streams[l], cudaStreamNonBlocking);
+        if (ce != cudaSuccess) {   // no room / no streams: fall back to the direct peer-store path
+          cudaGetLastError();
+          if (e->stage_buf) cudaFree(e->stage_buf), e->stage_buf = nullptr;
+          e->ce_chunks = 0;
+        }
+      }
     }
     if (const char* m = getenv("ACCFFT_B200_TMA")) e->tma_mode = m[0] == '0' ? 0 : m[0] == '2' ? 2 : m[0] == '3' ? 3 : 1;
     // ACCFFT_MEASURE / ACCFFT_PATIENT: pick the faster kernel per strided stage by timing both (plan-owned buffers only)
@@ -797,6 +879,21 @@ int accfftb_plan_stage_variant(const accfftb_plan* plan, int slot) {
 
 long long accfftb_plan_alloc_max(const accfftb_plan* plan) { return plan ? plan->e.plan.g.L.alloc_max : -1; }
 long long accfftb_plan_launch_count(const accfftb_plan* plan) { return plan ? plan->e.launches : -1; }
+long long accfftb_plan_copy_count(const accfftb_plan* plan) { return plan ? plan->e.copies : -1; }
+
+int accfftb_plan_check(accfftb_plan* plan) {
+  if (!plan) return fail(ACCFFTB_ERR_ARG, "null plan");
+  return engine_check(&plan->e);
+}
+
+int accfftb_plan_exchange_mode(const accfftb_plan* plan, int* chunks, int* lanes) {
+  if (!plan) return -1;
+  const Engine* e = &plan->e;
+  const bool ce = e->plan.nprocs > 1 && e->stage_buf && e->ce_chunks > 0 && e->ce_lanes > 0;
+  if (chunks) *chunks = ce ? e->ce_chunks : 0;
+  if (lanes) *lanes = ce ? e->ce_lanes : 0;
+  return ce ? 1 : 0;
+}
 
 int accfftb_plan_destroy(accfftb_plan* plan) {
   if (!plan) return 0;
@@ -813,7 +910,8 @@ int accfftb_plan_destroy(accfftb_plan* plan) {
   if ((want_r2c) && !(xyz & 4))                                                                      \
     return fail(ACCFFTB_ERR_UNSUPPORTED, "r2c / c2r need the Z axis selected: the real <-> complex step lives there " \
                                          "(the reference reinterprets the real rows as complex in that case)"); \
-  if (!(plan)->e.wired) return fail(ACCFFTB_ERR_STATE, "multi-rank plan used before its peers were attached");
+  if (!(plan)->e.wired) return fail(ACCFFTB_ERR_STATE, "multi-rank plan used before its peers were attached"); \
+  if (int dead__ = engine_check(&(plan)->e)) return dead__;
 
 int accfftb_execute_r2c(accfftb_plan* plan, const void* data, void* data_out, double* timer, int xyz) {
   CHECK_PLAN(plan, true);

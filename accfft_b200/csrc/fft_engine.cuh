@@ -22,6 +22,14 @@
 #define ACC_HD inline __attribute__((always_inline))
 #endif
 
+// out-of-line device functions (the spectral-operator multiply): ONE copy per translation unit instead of one inlined
+// copy per transform element and kernel -- the stage kernels shrank ~5x when apply_op left their bodies
+#if defined(__CUDACC__)
+#define ACC_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define ACC_HD_NOINLINE inline
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define ACC_UNROLL _Pragma("unroll")
 #else
@@ -183,6 +191,15 @@ ACC_HD cplx<T> mul_root(cplx<T> a) {
   }
 }
 
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
+template <int B, int E, class F>
+ACC_HD void static_for_idx(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for_idx<B + 1, E>(f);
+  }
+}
+
 // ---- small forward DFTs (sign -1), in place on v[0], v[S], v[2S], ... --------------------------
 template <int R, int S, class T> struct Dft;
 
@@ -234,6 +251,41 @@ template <int S, class T> struct Dft<5, S, T> {
   }
 };
 
+// generic odd prime P (7, 11, 13): pair the inputs j and P - j,
+//   X[k] , X[P-k] = (x0 + sum_j cos(2 pi j k / P) (x_j + x_(P-j)))  -+  i (sum_j sin(2 pi j k / P) (x_j - x_(P-j))),   j = 1 .. (P-1)/2
+// with compile-time cosines / sines: (P-1)^2 / 2 real FMAs per component instead of a full P x P complex product.
+template <int P, int S, class T>
+struct DftPrime {
+  static constexpr int H = (P - 1) / 2;
+  static ACC_HD void run(cplx<T>* v) {
+    const cplx<T> a0 = v[0];
+    cplx<T> s[H], d[H];
+    cplx<T> sum = a0;
+    static_for_idx<1, H + 1>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      s[j - 1] = cadd(v[j * S], v[(P - j) * S]);
+      d[j - 1] = csub(v[j * S], v[(P - j) * S]);
+      sum = cadd(sum, s[j - 1]);
+    });
+    v[0] = sum;
+    static_for_idx<1, H + 1>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      cplx<T> a = a0, b = {T(0), T(0)};
+      static_for_idx<1, H + 1>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr double c = root_re(P, j * k), sn = -root_im(P, j * k);
+        a = {a.x + T(c) * s[j - 1].x, a.y + T(c) * s[j - 1].y};
+        b = {b.x + T(sn) * d[j - 1].x, b.y + T(sn) * d[j - 1].y};
+      });
+      v[k * S] = {a.x + b.y, a.y - b.x};          // a - i b
+      v[(P - k) * S] = {a.x - b.y, a.y + b.x};    // a + i b
+    });
+  }
+};
+template <int S, class T> struct Dft<7, S, T> : DftPrime<7, S, T> {};
+template <int S, class T> struct Dft<11, S, T> : DftPrime<11, S, T> {};
+template <int S, class T> struct Dft<13, S, T> : DftPrime<13, S, T> {};
+
 // Cooley-Tukey composite R = R1*R2 entirely in registers:
 //   n = R2*n1 + n2, k = k1 + R1*k2 :  X[k1 + R1 k2] = sum_n2 W_R2^{n2 k2} W_R^{n2 k1} (sum_n1 x[R2 n1 + n2] W_R1^{n1 k1})
 // Output is written back in natural order (needs a register permutation, free after unrolling).
@@ -281,6 +333,7 @@ template <int S, class T> struct Dft<16, S, T> : DftCT<4, 4, S, T> {};
 template <int S, class T> struct Dft<9, S, T> : DftCT<3, 3, S, T> {};
 template <int S, class T> struct Dft<10, S, T> : DftCT<5, 2, S, T> {};
 template <int S, class T> struct Dft<15, S, T> : DftCT<5, 3, S, T> {};
+template <int S, class T> struct Dft<14, S, T> : DftCT<7, 2, S, T> {};
 
 // compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
 template <int B, int E, class F>

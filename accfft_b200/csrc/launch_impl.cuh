@@ -5,7 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include "kernel_cfg.hpp"
-#include "plan.hpp"
+#include "launch.hpp"
 #if ACCFFT_KIND == 4
 #include "stage_tma.cuh"
 #endif
@@ -33,31 +33,39 @@ struct CudaCtx {
   __device__ __forceinline__ void bulk_wait() const { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 };
 
-template <class T, class S>
-__global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS) k_strided_c2c(const __grid_constant__ StageDesc d) {
+// resident CTAs the contiguous kernels are compiled for: 1024 threads per SM (<= 64 registers per thread)
+constexpr int contig_minb(int threads) { return (1024 / threads) > 0 ? (1024 / threads) : 1; }
+
+// Every stage kernel is instantiated twice: GEN = false for "simple" stages (one local destination, no spectral operator,
+// no accumulation: everything a single-GPU transform launches) and GEN = true for the general case (peer segments, staged
+// bulk stores, operators, accumulation).  The simple instantiation carries none of that code.
+// (min blocks: 1024 resident threads per SM, i.e. <= 64 registers per thread, for both instantiations)
+template <class T, class S, bool GEN>
+__global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS, (1024 / Cfg<T, S>::STRIDED_THREADS) > 0 ? (1024 / Cfg<T, S>::STRIDED_THREADS) : 1)
+    k_strided_c2c(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  strided_c2c_body<T, S, Cfg<T, S>::TC>(d, ctx);
+  strided_c2c_body<T, S, Cfg<T, S>::TC, GEN>(d, ctx);
 }
 // same body, wide CTA shape (kernel_cfg.hpp: CfgW); instantiated only where it differs from the default shape
-template <class T, class S>
+template <class T, class S, bool GEN>
 __global__ void __launch_bounds__(CfgW<T, S>::STRIDED_THREADS, 1) k_strided_c2c_wide(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  strided_c2c_body<T, S, CfgW<T, S>::TC>(d, ctx);
+  strided_c2c_body<T, S, CfgW<T, S>::TC, GEN>(d, ctx);
 }
-template <class T, class S>
-__global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_c2c(const __grid_constant__ StageDesc d) {
+template <class T, class S, bool GEN>
+__global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS, contig_minb(Cfg<T, S>::CONTIG_THREADS)) k_contig_c2c(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  contig_c2c_body<T, S, Cfg<T, S>::PC>(d, ctx);
+  contig_c2c_body<T, S, Cfg<T, S>::PC, GEN>(d, ctx);
 }
-template <class T, class S>
-__global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_r2c(const __grid_constant__ StageDesc d) {
+template <class T, class S, bool GEN>
+__global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS, contig_minb(Cfg<T, S>::CONTIG_THREADS)) k_contig_r2c(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  contig_r2c_body<T, S, Cfg<T, S>::PC>(d, ctx);
+  contig_r2c_body<T, S, Cfg<T, S>::PC, GEN>(d, ctx);
 }
-template <class T, class S>
-__global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS) k_contig_c2r(const __grid_constant__ StageDesc d) {
+template <class T, class S, bool GEN>
+__global__ void __launch_bounds__(Cfg<T, S>::CONTIG_THREADS, contig_minb(Cfg<T, S>::CONTIG_THREADS)) k_contig_c2r(const __grid_constant__ StageDesc d) {
   CudaCtx ctx;
-  contig_c2r_body<T, S, Cfg<T, S>::PC>(d, ctx);
+  contig_c2r_body<T, S, Cfg<T, S>::PC, GEN>(d, ctx);
 }
 
 #ifndef ACCFFT_REAL_MINB
@@ -120,6 +128,18 @@ static int launch_kernel(K kernel, long long nblocks, int threads, int smem, con
   return (int)cudaGetLastError();
 }
 
+// launch the simple or the general instantiation of a stage kernel (dry runs load and configure both)
+template <class KS, class KG>
+static int launch_pair(KS simple_kernel, KG general_kernel, bool general, long long nblocks, int threads, int smem_simple,
+                       int smem_general, const StageDesc& d, cudaStream_t st, bool dry) {
+  if (dry) {
+    const int rc = launch_kernel(simple_kernel, nblocks, threads, smem_simple, d, st, true);
+    return rc ? rc : launch_kernel(general_kernel, nblocks, threads, smem_general, d, st, true);
+  }
+  return general ? launch_kernel(general_kernel, nblocks, threads, smem_general, d, st, false)
+                 : launch_kernel(simple_kernel, nblocks, threads, smem_simple, d, st, false);
+}
+
 #if ACCFFT_KIND != 4
 // staged stores can be switched off for A/B measurements: ACCFFT_B200_STAGED=0
 static bool staged_enabled() {
@@ -140,19 +160,23 @@ static int launch_one(const Launch& l, cudaStream_t st) {
 #else
   const StageDesc& d = l.desc;
 #endif
+  const bool gen = !stage_is_simple(d);
+  (void)gen;
 #if ACCFFT_KIND == 0
   if constexpr (C::HAS_WIDE) {
     using W = CfgW<T, S>;
     if (l.dry || l.variant == 3) {
       const long long nbw = (long long)d.nA * ((d.nB + d.colShift + W::TC - 1) / W::TC);
-      const int rc = launch_kernel(k_strided_c2c_wide<T, S>, nbw, W::STRIDED_THREADS, W::STRIDED_SMEM, d, st, l.dry);
+      const int rc = launch_pair(k_strided_c2c_wide<T, S, false>, k_strided_c2c_wide<T, S, true>, gen, nbw, W::STRIDED_THREADS,
+                                 W::STRIDED_SMEM, W::STRIDED_SMEM, d, st, l.dry);
       if (!l.dry || rc) return rc;
     }
   } else if (l.variant == 3 && !l.dry) {
     return -2;   // no wide shape for this length / precision: the caller falls back to the default shape
   }
   const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
-  return launch_kernel(k_strided_c2c<T, S>, nb, C::STRIDED_THREADS, C::STRIDED_SMEM, d, st, l.dry);
+  return launch_pair(k_strided_c2c<T, S, false>, k_strided_c2c<T, S, true>, gen, nb, C::STRIDED_THREADS, C::STRIDED_SMEM,
+                     C::STRIDED_SMEM, d, st, l.dry);
 #elif ACCFFT_KIND == 8
   const long long npairs = ((long long)d.nA * d.nB + 1) / 2;
   return launch_kernel(k_contig_deriv<T, S>, (npairs + C::PC - 1) / C::PC, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
@@ -168,13 +192,16 @@ static int launch_one(const Launch& l, cudaStream_t st) {
 #endif
 #elif ACCFFT_KIND == 1
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-  return launch_kernel(k_contig_c2c<T, S>, nb, C::CONTIG_THREADS, contig_smem, d, st, l.dry);
+  return launch_pair(k_contig_c2c<T, S, false>, k_contig_c2c<T, S, true>, gen, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, contig_smem,
+                     d, st, l.dry);
 #elif ACCFFT_KIND == 2
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-  return launch_kernel(k_contig_r2c<T, S>, nb, C::CONTIG_THREADS, contig_smem, d, st, l.dry);
+  return launch_pair(k_contig_r2c<T, S, false>, k_contig_r2c<T, S, true>, gen, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, contig_smem,
+                     d, st, l.dry);
 #else
   const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-  return launch_kernel(k_contig_c2r<T, S>, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
+  return launch_pair(k_contig_c2r<T, S, false>, k_contig_c2r<T, S, true>, gen, nb, C::CONTIG_THREADS, C::CONTIG_SMEM, C::CONTIG_SMEM,
+                     d, st, l.dry);
 #endif
 }
 
@@ -227,11 +254,15 @@ static int launch_tma(const Launch& l, cudaStream_t st) {
     return -2;
   } else {
     const StageDesc& d = l.desc;
-    auto kernel = k_strided_tma<T, S, C0::TC>;
+    const bool gen = !stage_is_simple(d);
+    auto kernel = gen ? k_strided_tma<T, S, C0::TC, true> : k_strided_tma<T, S, C0::TC, false>;
     if (l.dry) {
       cudaFuncAttributes fa;
-      cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+      cudaError_t e = cudaSuccess;
+      for (auto k : {k_strided_tma<T, S, C0::TC, false>, k_strided_tma<T, S, C0::TC, true>}) {
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+      }
       encode_tiled_fn();
       sm_count();
       return (int)e;

@@ -418,11 +418,171 @@ int Plan::forward_zy_pipelined(const void* in, bool in_padded, int nch) {
   return be->join();
 }
 
+// restrict a stage to the columns [b0, b0 + nb) of its (flat) inner index: unit column stride on both sides
+static Launch restrict_b(Launch l, int b0, int nb, size_t in_elem, size_t out_elem) {
+  StageDesc& d = l.desc;
+  d.in = (const char*)d.in + (long long)b0 * d.inStrideB * (long long)in_elem;
+  for (int s = 0; s < d.nseg; ++s) d.seg[s].base = (char*)d.seg[s].base + (long long)b0 * d.seg[s].strideB * (long long)out_elem;
+  d.nB = nb;
+  for (int ax = 0; ax < 3; ++ax)
+    if (d.kind[ax] == 2) d.off[ax] += b0;   // frequency index taken from the column index
+  return l;
+}
+
+int Plan::a_fence() {
+  if (!late_a_reader) return 0;
+  return nprocs > 1 ? bar() : 0;
+}
+
+// inter-rank barrier of the direct (peer-store) paths: any barrier also settles a pending late read of A
+int Plan::bar() {
+  late_a_reader = false;
+  return be->barrier();
+}
+
+// ================================================================================================================
+// Copy-engine exchange on slab grids (P1 == 1).  Reference analogue: the per-peer pipelined variants of its transposes,
+// fast_transpose_cuda_v1_2_h (src/transpose_gpu.cpp:2643-2673: per-peer cudaMemcpyAsync around MPI_Isend / Irecv) and
+// par::Mpi_Alltoallv_dense_gpu (include/parUtils.txx:165-384) -- there over PCIe and host memory, here device to device over
+// NVLink, with the pack fused into the producing FFT stage and no unpack at all.
+//
+// forward:  lane 1: [barrier F1]            copies(c=0) ...           copies(c=NCH-1)
+//           lane 0: Z(0) Y(0) | Z(1) Y(1) | ... | Z(NCH-1) Y(NCH-1) |        join, barrier F2, X
+//   Y(c) transforms the i0 rows of chunk c and stores the k1 block of peer q into staging_q (layout [i0][k1_q][pitch], exactly
+//   the sub-block of B_q this rank owns), its own k1 block straight into its own B.  One contiguous copy per (chunk, peer).
+// inverse:  lane 1: [barrier I0]      copies(c=0) ...        copies(c=NCH-1)
+//           lane 0: X(0) | X(1) | ... | X(NCH-1) |                  join, barrier I1, Y, Z
+//   X(c) transforms the columns of chunk c (flat (k1,k2) plane) and stores the i0 block of peer q into staging_q (layout
+//   [i0_q][plane]); one 2-D copy per (chunk, peer): i0_q rows of chunk-width bytes into A_q (row pitch N1 * k2).
+// Barriers: F1 / I0 ("every peer has finished its previous operation, so its B / A may be overwritten") run on the copy lane
+// and hide behind the first chunk's compute; F2 / I1 ("all copies have landed") are the only exposed ones.  On a slab grid
+// nothing else crosses ranks (Z and the inverse Y / Z are local), so a transform has 2 barriers instead of the direct path's 2
+// exposed ones, and the NVLink transfer overlaps the HBM-bound stages instead of running inside them.
+// ================================================================================================================
+int Plan::forward_slab_ce(const void* in, void* out, bool in_padded) {
+  int rc;
+  const size_t cs = prec == PREC_DOUBLE ? 16 : 8;
+  const size_t in_elem = g.r2c ? cs / 2 : cs;
+  const int P0 = g.np[0];
+  const int self = rank_of(g.np, g.coords[0], g.coords[1]);
+  const long long pk = pitch(g.k2.size);
+  const int n = g.i0.size;
+  int nch = be->ce_chunks();
+  if (nch > n) nch = n > 0 ? n : 1;
+  const int lanes = be->copy_lanes();
+  const Launch z = fwd_z(in, in_padded);
+  Launch y = fwd_y();
+  y.variant = be->local_variant(y);
+  // peers' k1 blocks go to the staging buffer, packed peer after peer
+  std::vector<long long> soff(P0, 0);
+  long long pos = 0;
+  for (int q = 0; q < P0; ++q) {
+    const int r = rank_of(g.np, q, g.coords[1]);
+    if (r == self) continue;
+    const Blk k1q = block_of(g.n[1], P0, q);
+    soff[q] = pos;
+    y.desc.seg[q].base = offs(be->staging(), pos, cs);   // strides unchanged: [i0][k1_q][pk]
+    pos += (long long)n * k1q.size * pk;
+  }
+  if ((rc = be->link(0, 1))) return rc;
+  if ((rc = be->barrier_on(1))) return rc;                       // F1
+  for (int l = 2; l <= lanes; ++l)
+    if ((rc = be->link(1, l))) return rc;
+  for (int c = 0; c < nch; ++c) {
+    const int a0 = (int)((long long)n * c / nch), a1 = (int)((long long)n * (c + 1) / nch);
+    if (a1 <= a0) continue;
+    Launch zc = restrict_a(z, a0, a1 - a0, in_elem, cs);
+    if (!empty(zc) && (rc = be->launch(zc))) return rc;
+    Launch yc = restrict_a(y, a0, a1 - a0, cs, cs);
+    if (!empty(yc) && (rc = be->launch(yc))) return rc;
+    for (int l = 1; l <= lanes && l < P0; ++l)
+      if ((rc = be->link(0, l))) return rc;
+    for (int i = 1; i < P0; ++i) {
+      const int q = (g.coords[0] + i) % P0;                      // every rank starts with a different peer
+      const int r = rank_of(g.np, q, g.coords[1]);
+      const Blk k1q = block_of(g.n[1], P0, q);
+      const long long row = (long long)k1q.size * pk;            // elements per i0 row of the block
+      if (row <= 0) continue;
+      void* dst = offs(peerB[r], ((long long)g.i0.start + a0) * row, cs);
+      const void* src = offs(be->staging(), soff[q] + (long long)a0 * row, cs);
+      const size_t bytes = (size_t)(a1 - a0) * (size_t)row * cs;
+      if ((rc = be->copy2d(1 + (i - 1) % lanes, dst, bytes, src, bytes, bytes, 1))) return rc;
+    }
+  }
+  for (int l = 1; l <= lanes; ++l)
+    if ((rc = be->link(l, 0))) return rc;
+  if ((rc = be->barrier())) return rc;                           // F2
+  late_a_reader = false;
+  Launch x = fwd_x(out);
+  if (!empty(x) && (rc = be->launch(x))) return rc;
+  return 0;
+}
+
+int Plan::inverse_slab_ce(const void* in, void* out, bool out_padded) {
+  int rc;
+  const size_t cs = prec == PREC_DOUBLE ? 16 : 8;
+  const int P0 = g.np[0];
+  const int self = rank_of(g.np, g.coords[0], g.coords[1]);
+  const long long plane = (long long)g.k1.size * g.k2.size;
+  const long long arow = (long long)g.n[1] * g.k2.size;          // elements per i0 row of A
+  int nch = be->ce_chunks();
+  const int lanes = be->copy_lanes();
+  Launch x = inv_x(in);
+  x.variant = be->local_variant(x);
+  std::vector<long long> soff(P0, 0);
+  long long pos = 0;
+  for (int q = 0; q < P0; ++q) {
+    const int r = rank_of(g.np, q, g.coords[1]);
+    if (r == self) continue;
+    const Blk i0q = block_of(g.n[0], P0, q);
+    soff[q] = pos;
+    x.desc.seg[q].base = offs(be->staging(), pos, cs);
+    x.desc.seg[q].strideI = plane;                               // staging rows are dense: [i0_q][plane]
+    pos += (long long)i0q.size * plane;
+  }
+  // chunk boundaries on multiples of 64 columns: tiles stay line aligned
+  const long long nblk = (plane + 63) / 64;
+  if (nch > nblk) nch = nblk > 0 ? (int)nblk : 1;
+  if ((rc = be->link(0, 1))) return rc;
+  if ((rc = be->barrier_on(1))) return rc;                       // I0
+  for (int l = 2; l <= lanes; ++l)
+    if ((rc = be->link(1, l))) return rc;
+  for (int c = 0; c < nch; ++c) {
+    const long long b0 = std::min(plane, nblk * c / nch * 64), b1 = std::min(plane, nblk * (c + 1) / nch * 64);
+    if (b1 <= b0) continue;
+    Launch xc = restrict_b(x, (int)b0, (int)(b1 - b0), cs, cs);
+    if (!empty(xc) && (rc = be->launch(xc))) return rc;
+    for (int l = 1; l <= lanes && l < P0; ++l)
+      if ((rc = be->link(0, l))) return rc;
+    for (int i = 1; i < P0; ++i) {
+      const int q = (g.coords[0] + i) % P0;
+      const int r = rank_of(g.np, q, g.coords[1]);
+      const Blk i0q = block_of(g.n[0], P0, q);
+      if (i0q.size <= 0) continue;
+      void* dst = offs(peerA[r], (long long)g.k1.start * g.k2.size + b0, cs);
+      const void* src = offs(be->staging(), soff[q] + b0, cs);
+      if ((rc = be->copy2d(1 + (i - 1) % lanes, dst, (size_t)arow * cs, src, (size_t)plane * cs, (size_t)(b1 - b0) * cs,
+                           (size_t)i0q.size)))
+        return rc;
+    }
+  }
+  for (int l = 1; l <= lanes; ++l)
+    if ((rc = be->link(l, 0))) return rc;
+  if ((rc = be->barrier())) return rc;                           // I1
+  Launch y = inv_y();
+  if (!empty(y) && (rc = be->launch(y))) return rc;
+  Launch z = inv_z(out, out_padded);
+  if (!empty(z) && (rc = be->launch(z))) return rc;
+  late_a_reader = true;   // Y read A after the last barrier: see a_fence()
+  return 0;
+}
+
 int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
   int rc;
+  if (use_ce(xyz)) return forward_slab_ce(in, out, in_padded);
   if (xyz == 7 && nprocs > 1 && g.np[1] == 1 && be->pipeline_chunks() > 1) {
     if ((rc = forward_zy_pipelined(in, in_padded, be->pipeline_chunks()))) return rc;
-    if ((rc = be->barrier())) return rc;
+    if ((rc = bar())) return rc;
     Launch x = fwd_x(out);
     if (!empty(x) && (rc = be->launch(x))) return rc;
     return 0;
@@ -430,11 +590,11 @@ int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
   Launch z = fwd_z(in, in_padded);
   if (!(xyz & 4)) no_transform(z, g.n[2]);
   if (!empty(z) && (rc = be->launch(z))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch y = fwd_y();
   if (!(xyz & 2)) no_transform(y, g.n[1]);
   if (!empty(y) && (rc = be->launch(y))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch x = fwd_x(out);
   if (!(xyz & 1)) no_transform(x, g.n[0]);
   if (!empty(x) && (rc = be->launch(x))) return rc;
@@ -443,14 +603,16 @@ int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
 
 int Plan::execute_inverse(const void* in, void* out, bool out_padded, int xyz) {
   int rc;
+  if (use_ce(xyz)) return inverse_slab_ce(in, out, out_padded);
+  if ((rc = a_fence())) return rc;
   Launch x = inv_x(in);
   if (!(xyz & 1)) no_transform(x, g.n[0]);
   if (!empty(x) && (rc = be->launch(x))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch y = inv_y();
   if (!(xyz & 2)) no_transform(y, g.n[1]);
   if (!empty(y) && (rc = be->launch(y))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch z = inv_z(out, out_padded);
   if (!(xyz & 4)) no_transform(z, g.n[2]);
   if (!empty(z) && (rc = be->launch(z))) return rc;
@@ -461,10 +623,10 @@ int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double
   int rc;
   Launch z = fwd_z(in, false);
   if (!empty(z) && (rc = be->launch(z))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch y = fwd_y();
   if (!empty(y) && (rc = be->launch(y))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   // X forward with the symbol multiply and the 1/N normalisation fused into its stores, into `spec`
   // (user spectrum layout), which the inverse X stage reads back
   Launch x = fwd_x(spec);
@@ -475,10 +637,10 @@ int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double
   if (!empty(x) && (rc = be->launch(x))) return rc;
   Launch xi = inv_x(spec);
   if (!empty(xi) && (rc = be->launch(xi))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch yi = inv_y();
   if (!empty(yi) && (rc = be->launch(yi))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch zi = inv_z(out, false);
   if (!empty(zi) && (rc = be->launch(zi))) return rc;
   return 0;
@@ -489,10 +651,10 @@ int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spe
   const double inv_n = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
   Launch z = fwd_z(in, false);
   if (!empty(z) && (rc = be->launch(z))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch y = fwd_y();
   if (!empty(y) && (rc = be->launch(y))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch x = fwd_x(spec);
   x.desc.op = OP_SCALE;
   x.desc.scale = inv_n;
@@ -506,10 +668,10 @@ int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spe
     xi.desc.opOnLoad = 1;
     xi.desc.opFullAxis = 1;
     if (!empty(xi) && (rc = be->launch(xi))) return rc;
-    if (nprocs > 1 && (rc = be->barrier())) return rc;
+    if (nprocs > 1 && (rc = bar())) return rc;
     Launch yi = inv_y();
     if (!empty(yi) && (rc = be->launch(yi))) return rc;
-    if (nprocs > 1 && (rc = be->barrier())) return rc;
+    if (nprocs > 1 && (rc = bar())) return rc;
     Launch zi = inv_z(outs[ax], false);
     if (!empty(zi) && (rc = be->launch(zi))) return rc;
   }
@@ -522,10 +684,10 @@ int Plan::execute_divergence(const void* const ins[3], void* out, void* spec) {
   for (int ax = 0; ax < 3; ++ax) {
     Launch z = fwd_z(ins[ax], false);
     if (!empty(z) && (rc = be->launch(z))) return rc;
-    if (nprocs > 1 && (rc = be->barrier())) return rc;
+    if (nprocs > 1 && (rc = bar())) return rc;
     Launch y = fwd_y();
     if (!empty(y) && (rc = be->launch(y))) return rc;
-    if (nprocs > 1 && (rc = be->barrier())) return rc;
+    if (nprocs > 1 && (rc = bar())) return rc;
     Launch x = fwd_x(spec);
     x.desc.op = OP_GRAD;
     x.desc.opAxis = ax;
@@ -536,10 +698,10 @@ int Plan::execute_divergence(const void* const ins[3], void* out, void* spec) {
   }
   Launch xi = inv_x(spec);
   if (!empty(xi) && (rc = be->launch(xi))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch yi = inv_y();
   if (!empty(yi) && (rc = be->launch(yi))) return rc;
-  if (nprocs > 1 && (rc = be->barrier())) return rc;
+  if (nprocs > 1 && (rc = bar())) return rc;
   Launch zi = inv_z(out, false);
   if (!empty(zi) && (rc = be->launch(zi))) return rc;
   return 0;
@@ -723,13 +885,14 @@ int Plan::execute_r2c_axis(int axis, const void* in, void* out) {
   }
   const bool ex = ax_exchanges(axis);
   if (ex) {
+    if ((rc = a_fence())) return rc;
     Launch c = ax_copy_in(axis, in);
     if (!empty(c) && (rc = be->launch(c))) return rc;
-    if ((rc = be->barrier())) return rc;
+    if ((rc = bar())) return rc;
   }
   Launch s = ax_stage(axis, AX_R2C, in, out);
   if (!empty(s) && (rc = be->launch(s))) return rc;
-  if (ex && (rc = be->barrier())) return rc;   // A was read after the exchange barrier: fence it from the next operation
+  if (ex && (rc = bar())) return rc;   // A was read after the exchange barrier: fence it from the next operation
   return 0;
 }
 
@@ -740,11 +903,11 @@ int Plan::execute_c2r_axis(int axis, const void* in, void* out) {
     return empty(z) ? 0 : be->launch(z);
   }
   const bool ex = ax_exchanges(axis);
-  if (ex && (rc = be->barrier())) return rc;   // B is written first thing: wait for the peers' previous operation
+  if (ex && (rc = bar())) return rc;   // B is written first thing: wait for the peers' previous operation
   Launch s = ax_stage(axis, AX_C2R, in, out);
   if (!empty(s) && (rc = be->launch(s))) return rc;
   if (ex) {
-    if ((rc = be->barrier())) return rc;
+    if ((rc = bar())) return rc;
     Launch c = ax_copy_out(out);
     if (!empty(c) && (rc = be->launch(c))) return rc;
   }
@@ -792,15 +955,16 @@ int Plan::execute_deriv_axis(int axis, const void* in, void* out, bool accumulat
   }
   const bool ex = ax_exchanges(axis);
   if (ex) {
+    if ((rc = a_fence())) return rc;
     Launch c = ax_copy_in(axis, in);
     if (!empty(c) && (rc = be->launch(c))) return rc;
-    if ((rc = be->barrier())) return rc;
+    if ((rc = bar())) return rc;
   }
   Launch s = ax_stage(axis, AX_DERIV, in, out);
   if (!ex) s.desc.accumulate = accumulate ? 1 : 0;
   if (!empty(s) && (rc = be->launch(s))) return rc;
   if (ex) {
-    if ((rc = be->barrier())) return rc;
+    if ((rc = bar())) return rc;
     Launch c = ax_copy_out(out);
     c.desc.accumulate = accumulate ? 1 : 0;
     if (!empty(c) && (rc = be->launch(c))) return rc;

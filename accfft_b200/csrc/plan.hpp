@@ -8,31 +8,9 @@
 #include <string>
 #include <vector>
 #include "decomp.hpp"
-#include "stage_real.cuh"
+#include "launch.hpp"
 
 namespace accfft_b200 {
-
-enum Kind : int {
-  K_STRIDED_C2C = 0, K_CONTIG_C2C = 1, K_CONTIG_R2C = 2, K_CONTIG_C2R = 3, K_COPY = 4,
-  // real transforms along a strided axis (stage_real.cuh): the single-axis executes and the per-axis derivative
-  K_STRIDED_R2C = 5, K_STRIDED_C2R = 6, K_STRIDED_DERIV = 7, K_COPY_REAL = 8,
-  K_CONTIG_DERIV = 9   // fused derivative along the contiguous (Z) axis: launcher translation unit k8
-};
-enum Prec : int { PREC_DOUBLE = 0, PREC_FLOAT = 1 };
-
-struct Launch {
-  Kind kind;
-  Prec prec;
-  int fftN;        // length of the complex engine transform (M = N/2 for r2c / c2r)
-  bool inverse;
-  bool dry;        // true: only load / configure the kernel (plan time), do not launch
-  int slot;        // profiling slot: 0 fwd Z, 1 fwd Y, 2 fwd X, 3 inv X, 4 inv Y, 5 inv Z  (6 = barrier),
-                   // 7 = real copy / exchange stages, 8 = single-axis real transform / derivative stages
-  long long copyN; // K_COPY_REAL: extent of the fastest input index k (a flat plane index on the x path)
-  int lane;        // 0 = the plan's stream, 1 = the plan's auxiliary stream (software-pipelined stages, see Backend::fork)
-  int variant;     // strided stages: 0 = backend's choice (plan-time tuning / heuristic), 1 = plain kernel, 2 = TMA-pipelined kernel
-  StageDesc desc;
-};
 
 // Device services of ONE rank.  The product implements this with CUDA (backend_cuda.cu); tests/emul
 // implements it with host memory and a fiber emulator (test infrastructure only).
@@ -54,6 +32,22 @@ struct Backend {
   virtual int hand(int) { return 0; }
   virtual int join() { return 0; }
   virtual int barrier_on(int) { return barrier(); }
+  // ---- copy-engine exchange (slab grids; Plan::forward_slab_ce / inverse_slab_ce) -------------------------------------------
+  // The exchanging stage writes its peer-bound output into a LOCAL staging buffer, laid out like the sub-blocks of the peers'
+  // buffers it is destined for; asynchronous copies (copy engines over NVLink: no SM involved) move chunk c while chunk c+1
+  // computes.  Lane 0 is the plan's stream, lanes 1 .. copy_lanes() are copy lanes.
+  //   ce_chunks()            chunks per exchanging stage; <= 0: the backend does not want the copy-engine path
+  //   copy_lanes()           number of copy lanes (copies to different peers proceed concurrently on different lanes)
+  //   staging()              this rank's staging buffer (at least one exchange buffer long)
+  //   link(from, to)         lane `to` waits for everything enqueued on lane `from` so far
+  //   copy2d(lane, ...)      enqueue a copy of `height` rows of `width` bytes (pitches in bytes) on a copy lane
+  //   local_variant(l)       the kernel variant tuned for this stage when it stores locally (see Launch::variant)
+  virtual int ce_chunks() { return 0; }
+  virtual int copy_lanes() { return 1; }
+  virtual void* staging() { return nullptr; }
+  virtual int link(int, int) { return 0; }
+  virtual int copy2d(int, void*, size_t, const void*, size_t, size_t, size_t) { return -1; }
+  virtual int local_variant(const Launch&) { return 0; }
 };
 
 struct Geometry {
@@ -131,6 +125,15 @@ struct Plan {
   int execute_forward(const void* in, void* out, bool in_padded, int xyz = 7);
   // slab grids (P1 == 1): the local Z stage and the exchanging Y stage software-pipelined over chunks of i0
   int forward_zy_pipelined(const void* in, bool in_padded, int nch);
+  // slab grids: exchange through a local staging buffer + copy-engine transfers, overlapped with the neighbouring stages
+  bool use_ce(int xyz) { return xyz == 7 && nprocs > 1 && g.np[1] == 1 && be->ce_chunks() > 0 && be->staging() != nullptr; }
+  int forward_slab_ce(const void* in, void* out, bool in_padded);
+  int inverse_slab_ce(const void* in, void* out, bool out_padded);
+  // The copy-engine inverse reads A after its last barrier.  Operations that write peers' A right at their start (the
+  // direct peer-store stages) fence against that with one extra barrier: see a_fence().
+  bool late_a_reader = false;
+  int a_fence();
+  int bar();
   int execute_inverse(const void* in, void* out, bool out_padded, int xyz = 7);
   // fused forward -> spectral symbol -> inverse (laplace / biharmonic; src/operators_gpu.txx:280-334, :555-609)
   int execute_spectral(const void* in, void* out, int op, void* spec, double opA = 0.0, double opB = 0.0);

@@ -106,8 +106,7 @@ ACC_HD int freq_index(const StageDesc& d, int ax, int k, int a, int b) {
 }
 
 template <class T>
-ACC_HD cplx<T> apply_op(const StageDesc& d, cplx<T> v, int k, int a, int b) {
-  if (d.op == OP_NONE) return v;
+ACC_HD_NOINLINE cplx<T> apply_op_impl(const StageDesc& d, cplx<T> v, int k, int a, int b) {
   if (d.op == OP_SCALE) return {T(v.x * d.scale), T(v.y * d.scale)};
   if (d.op == OP_GRAD) {
     // The reference differentiates with a REAL transform along the axis (src/operators_gpu.txx:172-278), i.e. it
@@ -146,7 +145,15 @@ ACC_HD cplx<T> apply_op(const StageDesc& d, cplx<T> v, int k, int a, int b) {
   return {T(w * v.x), T(w * v.y)};
 }
 
+// the symbol multiply itself is out of line (apply_op_impl); stages without an operator never make the call
+template <class T>
+ACC_HD cplx<T> apply_op(const StageDesc& d, cplx<T> v, int k, int a, int b) {
+  return d.op == OP_NONE ? v : apply_op_impl(d, v, k, a, b);
+}
+
 // true when the stage needs none of the generic machinery: one destination segment, no spectral operator
+// (every stage kernel exists in two instantiations: GEN = false serves exactly these stages -- the single-GPU transform --
+// and carries no segment / operator / accumulate code at all; GEN = true is the general kernel)
 ACC_HD bool stage_is_simple(const StageDesc& d) { return d.nseg == 1 && d.op == OP_NONE && d.accumulate == 0; }
 
 template <class T>
@@ -167,7 +174,7 @@ ACC_HD void store_generic(const StageDesc& d, cplx<T> y, int k, int a, int b) {
 // Used for the Y and X passes (reference: fplan_1 / fplan_2, src/accfft_gpu.cpp:208-253).
 // threads = S::G * TC;  tid -> (c = tid % TC, t = tid / TC);  smem layout [phys(i)][c]
 // ================================================================================================
-template <class T, class S, int TC, class Ctx>
+template <class T, class S, int TC, bool GEN, class Ctx>
 ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
   constexpr int G = S::G;
   constexpr int R0 = S::radix(0), NB0 = S::nb(0), CNT0 = S::cnt(0);
@@ -180,7 +187,6 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
   const int b = (int)(tile % tpa) * TC + c - d.colShift;
   const bool valid = b >= 0 && b < d.nB;
   const bool inv = d.inv != 0;
-  const bool simple = stage_is_simple(d);
   cplx<T> w1[S::NTW];
   load_base_twiddles<S, 1>(w1, t, (const cplx<T>*)d.tw);
   cplx<T> v[S::NREG];
@@ -199,7 +205,9 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
         for (int r = 0; r < R0; ++r) v[u * R0 + r] = ld_stream(p + r * step);
       }
     }
-    if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = apply_op(d, r, i, a, b); });
+    if constexpr (GEN) {
+      if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = apply_op(d, r, i, a, b); });
+    }
     if (inv) {
       ACC_UNROLL
       for (int i = 0; i < S::NREG; ++i) v[i] = cswap(v[i]);
@@ -212,7 +220,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
       ACC_UNROLL
       for (int i = 0; i < S::NREG; ++i) v[i] = cswap(v[i]);
     }
-    if (simple) {
+    if constexpr (!GEN) {
       const SegDst& sd = d.seg[0];
       cplx<T>* out = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
       const long long so = sd.strideI;
@@ -285,7 +293,7 @@ ACC_HD void staged_flush(const StageDesc& d, Ctx& ctx, const cplx<T>* stage, int
 // contiguous c2c: transform index has unit stride; PC pencils per CTA, G threads per pencil.
 // Used for the Z pass of c2c plans (reference fplan_0 of the c2c plan, src/accfft_gpu.cpp:767-790).
 // ================================================================================================
-template <class T, class S, int PC, class Ctx>
+template <class T, class S, int PC, bool GEN, class Ctx>
 ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
   const int tid = ctx.tid();
   const int t = tid % S::G, pcl = tid / S::G;
@@ -306,19 +314,23 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   cplx<T>* stage = (cplx<T>*)ctx.smem() + ((PC * S::SMEM_ELEMS + 1) & ~1);   // only touched when d.staged
   fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
-  if (valid) {
-    if (stage_is_simple(d)) {
+  if constexpr (!GEN) {
+    if (valid) {
       const SegDst& sd = d.seg[0];
       cplx<T>* out = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
       const long long so = sd.strideI;
       pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { st_stream(out + (long long)k * so, cswap_if(r, inv)); });
-    } else if (d.staged) {
-      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { stage[staged_index<PC>(d, S::N, pcl, k)] = cswap_if(r, inv); });
-    } else {
-      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, cswap_if(r, inv), k, a, b); });
     }
+  } else {
+    if (valid) {
+      if (d.staged) {
+        pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { stage[staged_index<PC>(d, S::N, pcl, k)] = cswap_if(r, inv); });
+      } else {
+        pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, cswap_if(r, inv), k, a, b); });
+      }
+    }
+    if (d.staged) staged_flush<T, PC>(d, ctx, stage, S::N, ctx.bid() * PC, S::G * PC);
   }
-  if (d.staged) staged_flush<T, PC>(d, ctx, stage, S::N, ctx.bid() * PC, S::G * PC);
 }
 
 // ================================================================================================
@@ -327,7 +339,7 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
 // S is the schedule of the M-point transform; d.tw is the table of N2 = 2M entries.
 // Input strides are in units of REAL elements and must be even.
 // ================================================================================================
-template <class T, class S, int PC, class Ctx>
+template <class T, class S, int PC, bool GEN, class Ctx>
 ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   constexpr int M = S::N;
   const int tid = ctx.tid();
@@ -358,14 +370,16 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   ctx.sync();
   if (valid) {
     constexpr int RL = S::radix(S::NP - 1), NBL = S::nb(S::NP - 1), CNTL = S::cnt(S::NP - 1);
-    const bool simple = stage_is_simple(d);
     const SegDst& s0 = d.seg[0];
     cplx<T>* out0 = (cplx<T>*)s0.base + (long long)a * s0.strideA + (long long)b * s0.strideB;
     const long long so = s0.strideI;
     auto put = [&](int kk, cplx<T> y) {
-      if (simple) st_stream(out0 + (long long)kk * so, y);
-      else if (d.staged) stage[staged_index<PC>(d, M + 1, pcl, kk)] = y;
-      else store_generic(d, y, kk, a, b);
+      if constexpr (!GEN) {
+        st_stream(out0 + (long long)kk * so, y);
+      } else {
+        if (d.staged) stage[staged_index<PC>(d, M + 1, pcl, kk)] = y;
+        else store_generic(d, y, kk, a, b);
+      }
     };
     // split step X[k] = (E + W_N2^k O)/2 for k = j + r*NBL:  W_N2^k = W_N2^j * W_(2 RL)^r, the second factor a
     // compile-time root, so only ws[u] = W_N2^j comes from the table (fetched up front)
@@ -392,7 +406,9 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
       }
     }
   }
-  if (d.staged) staged_flush<T, PC>(d, ctx, stage, M + 1, ctx.bid() * PC, S::G * PC);
+  if constexpr (GEN) {
+    if (d.staged) staged_flush<T, PC>(d, ctx, stage, M + 1, ctx.bid() * PC, S::G * PC);
+  }
 }
 
 // ================================================================================================
@@ -401,7 +417,7 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
 // Imaginary parts of X[0] and X[M] are ignored, as FFTW / cuFFT do.   Reference: iplan_0 = Z2D
 // (src/accfft_gpu.cpp:191-206).  Output strides (seg[0]) are in units of REAL elements and must be even.
 // ================================================================================================
-template <class T, class S, int PC, class Ctx>
+template <class T, class S, int PC, bool GEN, class Ctx>
 ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
   constexpr int M = S::N;
   const int tid = ctx.tid();
@@ -431,11 +447,13 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
         const int i = t + q * S::G;
         if (i <= M) x[q] = ld_stream(in + i);
       }
-      if (d.op != OP_NONE) {
-        ACC_UNROLL
-        for (int q = 0; q < NLD; ++q) {
-          const int i = t + q * S::G;
-          if (i <= M) x[q] = apply_op(d, x[q], i, a, b);
+      if constexpr (GEN) {
+        if (d.op != OP_NONE) {
+          ACC_UNROLL
+          for (int q = 0; q < NLD; ++q) {
+            const int i = t + q * S::G;
+            if (i <= M) x[q] = apply_op(d, x[q], i, a, b);
+          }
         }
       }
     }
@@ -480,7 +498,7 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
   if (valid) {
     const SegDst& sd = d.seg[0];
     cplx<T>* out = (cplx<T>*)((T*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB);
-    if (d.accumulate) {   // divergence: this component is added to what the earlier ones left in the output
+    if (GEN && d.accumulate) {   // divergence: this component is added to what the earlier ones left in the output
       pass_foreach<S, S::NP - 1>(v, t, [&](int nidx, cplx<T>& r) {
         const cplx<T> o = out[nidx];
         out[nidx] = {o.x + r.y, o.y + r.x};

@@ -143,7 +143,7 @@ __device__ __forceinline__ void tma_load_3d(void* sdst, const CUtensorMap* map, 
       : "memory");
 }
 
-template <class T, class S, int TC>
+template <class T, class S, int TC, bool GEN>
 __global__ void __launch_bounds__(TmaCfg<T, S, TC>::THREADS, TmaCfg<T, S, TC>::CTAS) k_strided_tma(const __grid_constant__ StageDesc d,
                                                                            const __grid_constant__ CUtensorMap tmap,
                                                                            long long ntiles) {
@@ -159,7 +159,6 @@ __global__ void __launch_bounds__(TmaCfg<T, S, TC>::THREADS, TmaCfg<T, S, TC>::C
   const int c0 = tid % TC, t0 = tid / TC;
   const int tpa = (d.nB + d.colShift + TC - 1) / TC;
   const bool inv = d.inv != 0;
-  const bool simple = stage_is_simple(d);
   constexpr int E = C::ES / 8;   // tensor-map elements (u64) per complex value
 
   auto issue = [&](int i) {   // elected thread: start the loads of this CTA's i-th tile
@@ -206,7 +205,9 @@ __global__ void __launch_bounds__(TmaCfg<T, S, TC>::THREADS, TmaCfg<T, S, TC>::C
         for (int r = 0; r < R0; ++r) v[u * R0 + r] = sm[(j + r * NB0) * TC + c];
       }
     }
-    if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int k, cplx<T>& r) { r = apply_op(d, r, k, a, b); });
+    if constexpr (GEN) {
+      if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int k, cplx<T>& r) { r = apply_op(d, r, k, a, b); });
+    }
     if (inv) {
 #pragma unroll
       for (int k = 0; k < S::NREG; ++k) v[k] = cswap(v[k]);
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(TmaCfg<T, S, TC>::THREADS, TmaCfg<T, S, TC>::C
 #pragma unroll
         for (int k = 0; k < S::NREG; ++k) v[k] = cswap(v[k]);
       }
-      if (simple) {
+      if constexpr (!GEN) {
         const SegDst& sd = d.seg[0];
         cplx<T>* out = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
         const long long so = sd.strideI;

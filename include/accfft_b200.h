@@ -110,9 +110,10 @@ int accfftb_plan_set_blocking(accfftb_plan* plan, int blocking);
  * the plan's stream (no host synchronisation).  _profile_read synchronises the stream, returns the summed
  * milliseconds and launch counts per slot since the last read, and resets.  Slots: 0 forward Z pass,
  * 1 forward Y, 2 forward X, 3 inverse X, 4 inverse Y, 5 inverse Z, 6 inter-GPU barrier, 7 real copy / exchange
- * stages of the single-axis paths, 8 single-axis transform / derivative stages.  (The reference only offers the
- * coarse timer[5] of doc/timing.md.) */
-#define ACCFFTB_PROFILE_SLOTS 9
+ * stages of the single-axis paths, 8 single-axis transform / derivative stages, 9 copy-engine transfers of the slab
+ * exchange (event pairs on the copy lanes; transfers on different lanes overlap, so their sum can exceed wall time).
+ * (The reference only offers the coarse timer[5] of doc/timing.md.) */
+#define ACCFFTB_PROFILE_SLOTS 10
 int accfftb_plan_set_profiling(accfftb_plan* plan, int on);
 int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOTS], long long count[ACCFFTB_PROFILE_SLOTS]);
 
@@ -127,6 +128,23 @@ int accfftb_plan_stage_variant(const accfftb_plan* plan, int slot);
 long long accfftb_plan_alloc_max(const accfftb_plan* plan);
 /* number of kernels the plan has launched so far (stage kernels + inter-GPU barrier kernels) */
 long long accfftb_plan_launch_count(const accfftb_plan* plan);
+/* number of copy-engine transfers (cudaMemcpy[2D]Async between exchange buffers) the plan has enqueued so far */
+long long accfftb_plan_copy_count(const accfftb_plan* plan);
+
+/* How the plan exchanges data between GPUs.  Returns 1 for the copy-engine exchange -- slab grids (P1 == 1): the exchanging
+ * FFT stage packs into a local staging buffer, chunk by chunk, and asynchronous device-to-device copies over NVLink move
+ * chunk c while chunk c+1 computes (the reference's closest relatives: fast_transpose_cuda_v1_2_h,
+ * src/transpose_gpu.cpp:2643-2673, and par::Mpi_Alltoallv_dense_gpu, include/parUtils.txx:165-384, both host staged) --
+ * and 0 for direct peer stores fused into the FFT kernels (pencil grids, single-rank plans, ACCFFT_B200_CE=0).
+ * chunks / lanes (may be NULL) receive the chunk count and the number of concurrent copy streams. */
+int accfftb_plan_exchange_mode(const accfftb_plan* plan, int* chunks, int* lanes);
+
+/* Health of a multi-GPU plan, WITHOUT synchronising anything: 0, or ACCFFTB_ERR_TIMEOUT once an inter-GPU barrier of the
+ * plan has timed out (a peer died or issued a different sequence of calls).  The condition is sticky: the stages after
+ * that barrier ran on incomplete data, so every later call on the plan fails with the same code before launching
+ * anything -- in blocking and non-blocking mode alike.  Callers that drive the plan with blocking = 0 should poll this
+ * after their own stream synchronisation.  Time-out: 10 s of SM clock (ACCFFT_B200_BARRIER_TIMEOUT_MS overrides). */
+int accfftb_plan_check(accfftb_plan* plan);
 
 /* accfft_destroy_plan_gpu / accfft_destroy_plan (src/accfft_gpu.cpp:1150-1192); frees everything the
  * plan owns (the reference leaks the plan object and T_plan_x/xi).  NULL is accepted. */

@@ -115,6 +115,22 @@ struct EmuBackend : Backend {
     const char* c = getenv("EMU_PIPELINE_CHUNKS");
     return c ? atoi(c) : 1;
   }
+  // copy-engine exchange (Plan::forward_slab_ce / inverse_slab_ce): copies are row memcpys executed in program order
+  std::vector<char> stage_buf;
+  int ce_chunks() override {
+    const char* c = getenv("EMU_CE_CHUNKS");
+    return c ? atoi(c) : 0;
+  }
+  int copy_lanes() override {
+    const char* c = getenv("EMU_CE_LANES");
+    return c ? atoi(c) : 2;
+  }
+  void* staging() override { return stage_buf.empty() ? nullptr : stage_buf.data(); }
+  int copy2d(int lane, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) override {
+    if (lane < 1 || lane > copy_lanes()) return -1;
+    for (size_t r = 0; r < height; ++r) memcpy((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+    return 0;
+  }
 };
 
 struct EmuWorld {
@@ -162,6 +178,7 @@ void* emu_world_create(const int* n, int P0, int P1, int r2c, int prec) {
     w->bufA[r].assign(bb + 64, (char)0xEE);
     w->bufB[r].assign(bb + 64, (char)0xEE);
     w->spec[r].assign(bb + 64, (char)0xEE);
+    w->be[r].stage_buf.assign(bb + 64, (char)0xEE);
   }
   for (int r = 0; r < w->nprocs; ++r) {
     Plan& p = w->plans[r];

@@ -16,7 +16,7 @@ MAIN_SOURCES = [os.path.join(HERE, "emul.cpp"), os.path.join(ROOT, "accfft_b200"
 PART_SOURCE = os.path.join(HERE, "emul_part.cpp")
 SOURCES = MAIN_SOURCES + [PART_SOURCE, os.path.join(HERE, "emul_fiber.hpp")]
 HEADERS = [os.path.join(ROOT, "accfft_b200", "csrc", f)
-           for f in ("fft_engine.cuh", "stage.cuh", "stage_real.cuh", "plan.hpp", "decomp.hpp", "kernel_cfg.hpp", "schedules.def")]
+           for f in ("fft_engine.cuh", "stage.cuh", "stage_real.cuh", "plan.hpp", "launch.hpp", "decomp.hpp", "kernel_cfg.hpp", "schedules.def")]
 
 sys.path.insert(0, ROOT)
 from oracle import accfft_oracle as orc  # noqa: E402

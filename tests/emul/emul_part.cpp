@@ -14,29 +14,42 @@ template <class T, class S>
 static void emu_launch_sched(const Launch& l) {
   using C = Cfg<T, S>;
   const StageDesc& d = l.desc;
+  const bool gen = !stage_is_simple(d);   // the same choice the CUDA launchers make (launch_impl.cuh: launch_pair)
   switch (l.kind) {
     case K_STRIDED_C2C: {
       const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
-      run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) { strided_c2c_body<T, S, C::TC>(d, c); });
+      run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) {
+        if (gen) strided_c2c_body<T, S, C::TC, true>(d, c);
+        else strided_c2c_body<T, S, C::TC, false>(d, c);
+      });
       break;
     }
     case K_CONTIG_C2C: {
       const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
       StageDesc ds = d;
       ds.staged = (d.nseg > 1 && d.op == OP_NONE && d.accumulate == 0) ? 1 : 0;
-      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_STAGED_SMEM, [&](EmuCtx& c) { contig_c2c_body<T, S, C::PC>(ds, c); });
+      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_STAGED_SMEM, [&](EmuCtx& c) {
+        if (gen) contig_c2c_body<T, S, C::PC, true>(ds, c);
+        else contig_c2c_body<T, S, C::PC, false>(ds, c);
+      });
       break;
     }
     case K_CONTIG_R2C: {
       const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
       StageDesc ds = d;
       ds.staged = (d.nseg > 1 && d.op == OP_NONE && d.accumulate == 0) ? 1 : 0;
-      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_STAGED_SMEM, [&](EmuCtx& c) { contig_r2c_body<T, S, C::PC>(ds, c); });
+      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_STAGED_SMEM, [&](EmuCtx& c) {
+        if (gen) contig_r2c_body<T, S, C::PC, true>(ds, c);
+        else contig_r2c_body<T, S, C::PC, false>(ds, c);
+      });
       break;
     }
     case K_CONTIG_C2R: {
       const long long nb = ((long long)d.nA * d.nB + C::PC - 1) / C::PC;
-      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) { contig_c2r_body<T, S, C::PC>(d, c); });
+      run_grid(nb, C::CONTIG_THREADS, C::CONTIG_SMEM, [&](EmuCtx& c) {
+        if (gen) contig_c2r_body<T, S, C::PC, true>(d, c);
+        else contig_c2r_body<T, S, C::PC, false>(d, c);
+      });
       break;
     }
     case K_CONTIG_DERIV: {

@@ -240,4 +240,52 @@ def test_seeded_random_sweep_single_precision():
 
 def test_unsupported_length_is_refused():
     with pytest.raises(RuntimeError):
-        emu.World((7, 8, 8), (1, 1), r2c=True)
+        emu.World((17, 8, 8), (1, 1), r2c=True)
+
+
+@pytest.mark.parametrize("chunks,lanes", [(1, 1), (3, 2), (16, 7)])
+@pytest.mark.parametrize("n,np_", [((16, 12, 20), (2, 1)), ((12, 10, 16), (4, 1)), ((5, 6, 6), (4, 1)), ((3, 5, 4), (4, 1)),
+                                   ((32, 24, 20), (8, 1))])
+def test_copy_engine_slab_exchange(monkeypatch, n, np_, chunks, lanes):
+    """Plan::forward_slab_ce / inverse_slab_ce (staging buffer + chunked copies instead of peer stores) on slab grids:
+    same spectra as the direct path, also when mixed with operations that still use peer stores (operators, single-axis
+    transforms) -- the late-A-reader fence of plan.cpp"""
+    monkeypatch.setenv("EMU_CE_CHUNKS", str(chunks))
+    monkeypatch.setenv("EMU_CE_LANES", str(lanes))
+    x = orc.synthetic_real(n, 7)
+    X = orc.forward_r2c(x)
+    w = emu.World(n, np_, r2c=True)
+    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), X) < 1e-12
+    for _ in range(2):   # inverse after inverse: the second one's copies must wait for the first one's late reads of A
+        assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, np_), x * x.size) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.spectral(x, "laplace"), n, np_), orc.laplace(x)) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, np_), x * x.size) < 1e-12
+    g = emu.grad(w, x, fast=True)
+    for ax in range(3):
+        assert orc.rel_l2(orc.assemble_input(g[ax], n, np_), orc.grad(x, ax)) < 1e-12
+    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), X) < 1e-12
+    w.close()
+    z = orc.synthetic_complex(n, 8)
+    Z = orc.forward_c2c(z)
+    w = emu.World(n, np_, r2c=False)
+    assert orc.rel_l2(orc.assemble_output(w.forward(z), n, np_, r2c=False), Z) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.inverse(Z), n, np_), z * z.size) < 1e-12
+    w.close()
+
+
+@pytest.mark.parametrize("n,np_", [((7, 14, 22), (1, 1)), ((49, 13, 26), (1, 1)), ((28, 11, 14), (2, 2)), ((13, 7, 98), (1, 2)),
+                                   ((56, 44, 28), (2, 1))])
+def test_radix_7_11_13_lengths(n, np_):
+    """prime radices 7 / 11 / 13 (fft_engine.cuh: DftPrime) and the composite 14"""
+    x = orc.synthetic_real(n, 71)
+    X = orc.forward_r2c(x)
+    w = emu.World(n, np_, r2c=True)
+    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), X) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, np_), x * x.size) < 1e-12
+    w.close()
+    z = orc.synthetic_complex(n, 72)
+    Z = orc.forward_c2c(z)
+    w = emu.World(n, np_, r2c=False)
+    assert orc.rel_l2(orc.assemble_output(w.forward(z), n, np_, r2c=False), Z) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.inverse(Z), n, np_), z * z.size) < 1e-12
+    w.close()

@@ -67,7 +67,10 @@ SIZES = [(8, 8, 8), (16, 12, 20), (2, 2, 2), (4, 6, 10), (5, 3, 8), (32, 48, 64)
          (4, 6, 2048), (1024, 12, 8), (8, 768, 12), (1536, 4, 6),
          # b, c = 3 families: decimal grids and 27-multiples (G up to 200 threads per column)
          (125, 27, 250), (4, 6, 2000), (1000, 8, 12), (12, 1728, 8), (500, 6, 54), (8, 1500, 10), (6, 10, 1728), (216, 432, 108),
-         (135, 270, 6), (375, 4, 540), (8, 675, 750), (1080, 6, 4), (4, 1125, 6), (6, 4, 1350), (864, 4, 6), (450, 6, 4)]
+         (135, 270, 6), (375, 4, 540), (8, 675, 750), (1080, 6, 4), (4, 1125, 6), (6, 4, 1350), (864, 4, 6), (450, 6, 4),
+         # prime radices 7 / 11 / 13, the composite 14, and 4096-long axes (three radix-16 passes, 256 threads per column)
+         (7, 14, 22), (49, 13, 26), (28, 44, 98), (448, 6, 56), (6, 1792, 8), (4, 6, 1456), (12, 10, 14),
+         (4096, 4, 6), (6, 4096, 4), (4, 6, 8192)]
 
 
 @pytest.mark.parametrize("n", SIZES)
@@ -457,8 +460,8 @@ def test_error_behaviour(cuda_device):
     comm = acc.Comm(0, 1, (1, 1))
     with pytest.raises(acc.AccfftError):     # odd N2 for r2c
         acc.accfft_plan_dft_3d_r2c_gpu((8, 8, 9), comm)
-    with pytest.raises(acc.AccfftError):     # no schedule for 7
-        acc.accfft_plan_dft_3d_c2c_gpu((7, 8, 8), comm)
+    with pytest.raises(acc.AccfftError):     # no schedule for 17
+        acc.accfft_plan_dft_3d_c2c_gpu((17, 8, 8), comm)
     p = acc.accfft_plan_dft_3d_r2c_gpu((8, 8, 8), comm)
     x = torch.zeros(8 * 8 * 8, dtype=torch.float64, device=cuda_device)
     out = alloc_out(p, False, cuda_device)
@@ -481,6 +484,87 @@ def test_error_behaviour(cuda_device):
         q.execute_r2c(x, out)
     acc.lib().accfftb_plan_destroy(q._h)
     q._h = None
+
+
+def test_barrier_timeout_is_sticky_and_visible_without_blocking(cuda_device, monkeypatch):
+    """A rank whose peers never arrive: the barrier kernel times out, the status word is sticky, and every later call fails
+    with ACCFFTB_ERR_TIMEOUT -- in non-blocking mode too (accfftb_plan_check / the next call), not only after a blocking
+    synchronise (round-1 finding: non-blocking plans silently ran on stale peer data)."""
+    torch = torch_mod()
+    monkeypatch.setenv("ACCFFT_B200_BARRIER_TIMEOUT_MS", "100")
+    n = (16, 12, 20)
+    comms = [acc.Comm(r, 2, (2, 1)) for r in range(2)]
+    plans = [acc.Plan(n, comms[r], r2c=True, single=False, wire=False) for r in range(2)]
+    acc.attach_local_peers(plans)
+    p = plans[0]
+    x = torch.zeros(p.isize[0] * p.isize[1] * p.isize[2], dtype=torch.float64, device=cuda_device)
+    out = alloc_out(p, False, cuda_device)
+    p.check()                                   # healthy
+    p.set_blocking(False)
+    p.execute_r2c(x, out)                       # rank 1 never calls: rank 0's barriers time out on the device
+    torch.cuda.synchronize()
+    with pytest.raises(acc.AccfftError, match="timed out"):
+        p.check()
+    with pytest.raises(acc.AccfftError, match="timed out"):
+        p.execute_r2c(x, out)                   # refused before anything is launched
+    p.set_blocking(True)
+    with pytest.raises(acc.AccfftError, match="timed out"):
+        p.execute_c2r(out, x)
+    for q in plans:
+        acc.lib().accfftb_plan_destroy(q._h)
+        q._h = None
+
+
+@pytest.mark.parametrize("n,dims,r2c", [((16, 12, 20), (2, 1), True), ((64, 48, 40), (4, 1), True), ((5, 6, 6), (4, 1), True),
+                                        ((32, 24, 20), (8, 1), False), ((128, 96, 80), (2, 1), True)])
+def test_copy_engine_exchange_matches_peer_stores_bitwise(cuda_device, monkeypatch, n, dims, r2c):
+    """slab grids: the copy-engine exchange (default) and the direct peer-store exchange (ACCFFT_B200_CE=0) run the same
+    kernels on the same data in the same order per element, so spectra and round trips agree BITWISE"""
+    torch = torch_mod()
+    nprocs = dims[0] * dims[1]
+    x = orc.synthetic_real(n, 41) if r2c else orc.synthetic_complex(n, 41)
+    results = {}
+    for mode, env in (("ce", {"ACCFFT_B200_CE": "3", "ACCFFT_B200_CE_LANES": "2"}), ("direct", {"ACCFFT_B200_CE": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        comms = [acc.Comm(r, nprocs, dims) for r in range(nprocs)]
+        plans = [acc.Plan(n, comms[r], r2c=r2c, single=False, wire=False, flags=acc.ACCFFT_ESTIMATE) for r in range(nprocs)]
+        acc.attach_local_peers(plans)
+        assert plans[0].exchange_mode()["mode"] == ("copy_engine" if mode == "ce" else "peer_store")
+        streams = [torch.cuda.Stream() for _ in range(nprocs)]
+        ins, outs, backs = [], [], []
+        for r in range(nprocs):
+            loc = orc.local_input(x, n, dims, comms[r].coords)
+            t = to_dev(loc, cuda_device) if loc.size else torch.zeros(2, dtype=torch.float64, device=cuda_device)
+            ins.append(torch.view_as_real(t).contiguous() if (not r2c and loc.size) else t)
+            outs.append(torch.zeros(max(plans[r].alloc_max // 8, 2), dtype=torch.float64, device=cuda_device))
+            backs.append(torch.zeros_like(ins[-1]))
+            plans[r].set_stream(streams[r].cuda_stream)
+        torch.cuda.synchronize()
+
+        def body(r):
+            with torch.cuda.stream(streams[r]):
+                for _ in range(3):
+                    if r2c:
+                        plans[r].execute_r2c(ins[r], outs[r])
+                        plans[r].execute_c2r(outs[r], backs[r])
+                    else:
+                        plans[r].execute_c2c(acc.ACCFFT_FORWARD, ins[r], outs[r])
+                        plans[r].execute_c2c(acc.ACCFFT_BACKWARD, outs[r], backs[r])
+
+        run_ranks(nprocs, body)
+        torch.cuda.synchronize()
+        if mode == "ce":
+            assert plans[0].copy_count > 0
+        results[mode] = ([o.cpu().numpy().copy() for o in outs], [b.cpu().numpy().copy() for b in backs])
+        blocks = [outs[r].cpu().numpy().view(np.complex128)[:int(np.prod(plans[r].osize))].reshape(plans[r].osize) for r in range(nprocs)]
+        X = orc.forward_r2c(x) if r2c else orc.forward_c2c(x)
+        assert orc.rel_l2(orc.assemble_output(blocks, n, dims, r2c=r2c), X) <= 1e-12
+        for p in plans:
+            acc.lib().accfftb_plan_destroy(p._h)
+            p._h = None
+    for a, b in zip(results["ce"][0] + results["ce"][1], results["direct"][0] + results["direct"][1]):
+        assert np.array_equal(a, b)
 
 
 def test_timer_accumulates_and_launch_count(cuda_device):
