@@ -24,6 +24,7 @@ from .api import (  # noqa: F401
     accfft_plan_dft_3d_c2c_gpuf,
     accfft_plan_dft_3d_r2c_gpu,
     accfft_plan_dft_3d_r2c_gpuf,
+    length_fast,
     length_supported,
     lib,
     lib_path,

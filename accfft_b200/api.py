@@ -63,6 +63,7 @@ def lib():
         f.argtypes = [ip, ip, ip, c_int, ip, ip, ip, ip]
     L.accfftb_stage_size.argtypes = [ip, ip, ip, c_int, c_int, c_int, ip, ip]
     L.accfftb_length_supported.argtypes = [c_int]
+    L.accfftb_length_fast.argtypes = [c_int]
     L.accfftb_plan_create.restype = c_vp
     L.accfftb_plan_create.argtypes = [ip, ip, c_int, c_int, c_int, ctypes.c_uint]
     L.accfftb_plan_ipc_export.argtypes = [c_vp, c_vp]
@@ -118,7 +119,13 @@ def _i2(v: Sequence[int]):
 
 
 def length_supported(n: int) -> bool:
+    """can an axis of this length be planned (scheduled kernel or the generic O(n^2) fallback)?"""
     return bool(lib().accfftb_length_supported(int(n)))
+
+
+def length_fast(n: int) -> bool:
+    """does a compiled Stockham schedule exist for this complex length?"""
+    return bool(lib().accfftb_length_fast(int(n)))
 
 
 class Comm:

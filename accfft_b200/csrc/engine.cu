@@ -40,6 +40,8 @@ int accfft_launch_k7_p0(const Launch&, cudaStream_t);
 int accfft_launch_k7_p1(const Launch&, cudaStream_t);
 int accfft_launch_k8_p0(const Launch&, cudaStream_t);   // contiguous (Z-axis) derivative
 int accfft_launch_k8_p1(const Launch&, cudaStream_t);
+int accfft_launch_generic(const Launch&, int realN, cudaStream_t);   // generic_dft.cu: O(N^2) fallback, -1 = not served
+int accfft_generic_max_length(Prec prec);
 int accfft_has_wide_p0(int n);   // does the strided kernel have a wide CTA shape for this length? (k_tu.cu, kind 0)
 int accfft_has_wide_p1(int n);
 static bool has_wide(Prec p, int n) { return (p == PREC_DOUBLE ? accfft_has_wide_p0(n) : accfft_has_wide_p1(n)) != 0; }
@@ -155,6 +157,7 @@ struct Engine;
 struct CudaBackend : Backend {
   Engine* e = nullptr;
   bool supported(Kind, Prec, int fftN) override { return length_supported(fftN); }
+  bool generic_ok(Prec prec, int N) override { return N >= 1 && N <= accfft_generic_max_length(prec); }
   const void* twiddle(Prec prec, int tableN) override;
   int launch(const Launch& l) override;
   int barrier() override;
@@ -385,6 +388,19 @@ int CudaBackend::launch(const Launch& l) {
     e->launches++;
     return 0;
   }
+  // lengths without a compiled schedule, and r2c / c2r with an odd real length: the generic O(N^2) stage kernel
+  {
+    const bool real_kind = l.kind == K_CONTIG_R2C || l.kind == K_CONTIG_C2R;
+    const int realN = e->plan.g.n[2];
+    const bool complex_kind = l.kind == K_STRIDED_C2C || l.kind == K_CONTIG_C2C;
+    if ((real_kind && (realN % 2 != 0 || !length_supported(l.fftN))) || (complex_kind && !length_supported(l.fftN))) {
+      const int grc = accfft_launch_generic(l, realN, e->stream);
+      if (grc == -1) return fail(ACCFFTB_ERR_UNSUPPORTED, "no kernel for length " + std::to_string(real_kind ? realN : l.fftN));
+      if (grc != 0) return cuda_fail((cudaError_t)grc, "generic stage kernel launch");
+      if (!l.dry) e->launches++;
+      return 0;
+    }
+  }
   const int sel = (int)l.kind * 2 + (int)l.prec;
   switch (sel) {
     case 0:
@@ -559,10 +575,12 @@ static int autotune(Engine* e) {
   int rc = 0;
   for (Launch& l : ls) {
     StageDesc& d = l.desc;
-    if (d.nA <= 0 || d.nB <= 0) continue;
-    if (d.nseg > 1) {   // stores to peers: NVLink-bound, not tunable on this rank alone -- see CudaBackend::launch
+    if (d.nA <= 0 || d.nB <= 0 || !length_supported(l.fftN)) continue;
+    const bool to_peers = d.nseg > 1;
+    if (to_peers) {   // stores to peers: NVLink-bound, not tunable on this rank alone -- see CudaBackend::launch
       e->variant[l.slot] = has_wide(l.prec, l.fftN) ? 3 : 1;   // wide shape where the length has one, else the plain kernel
-      continue;
+      // copy-engine exchange: the same stage packs into LOCAL staging instead -- tune it like a local stage (variant_local)
+      if (!(e->ce_chunks > 0 && e->stage_buf)) continue;
     }
     // single local destination [a][k][b]: same bytes as the stage input, which fits one exchange buffer
     d.nseg = 1;
@@ -589,7 +607,9 @@ static int autotune(Engine* e) {
     }
     if (rc) break;
     if (!has_wide(l.prec, l.fftN)) best[3] = 1e30f;   // that run fell back to the plain kernel
-    e->variant[l.slot] = best[2] < best[1] ? (best[3] < best[2] ? 3 : 2) : (best[3] < best[1] ? 3 : 1);
+    const int pick = best[2] < best[1] ? (best[3] < best[2] ? 3 : 2) : (best[3] < best[1] ? 3 : 1);
+    if (to_peers) e->variant_local[l.slot] = pick;
+    else e->variant[l.slot] = pick;
   }
   cudaEventDestroy(a);
   cudaEventDestroy(b);
@@ -673,7 +693,8 @@ int accfftb_stage_size(const int n[3], const int c_dims[2], const int coords[2],
   }
 }
 
-int accfftb_length_supported(int n) { return length_supported(n) ? 1 : 0; }
+int accfftb_length_supported(int n) { return (length_supported(n) || (n >= 1 && n <= accfft_generic_max_length(PREC_DOUBLE))) ? 1 : 0; }
+int accfftb_length_fast(int n) { return length_supported(n) ? 1 : 0; }
 
 accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank, int kind, int prec, unsigned flags) {
   if (!n || !c_dims || n[0] <= 0 || n[1] <= 0 || n[2] <= 0 || c_dims[0] <= 0 || c_dims[1] <= 0 || rank < 0 ||
@@ -861,10 +882,30 @@ int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOT
   Engine* e = &plan->e;
   CU(cudaStreamSynchronize(e->stream));
   for (int i = 0; i < ACCFFTB_PROFILE_SLOTS; ++i) ms[i] = 0, count[i] = 0;
+  // slot 9 (copy-engine transfers): transfers on different lanes overlap, so report the UNION of their intervals -- the
+  // time during which at least one transfer was in flight -- not the sum
+  std::vector<std::pair<float, float>> spans;
+  cudaEvent_t ref = nullptr;
   for (auto& r : e->recs) {
     float t = 0;
     CU(cudaEventElapsedTime(&t, r.a, r.b));
-    if (r.slot >= 0 && r.slot < ACCFFTB_PROFILE_SLOTS) ms[r.slot] += t, count[r.slot]++;
+    if (r.slot == 9) {
+      if (!ref) ref = r.a;
+      float t0 = 0;
+      CU(cudaEventElapsedTime(&t0, ref, r.a));
+      spans.push_back({t0, t0 + t});
+      count[9]++;
+    } else if (r.slot >= 0 && r.slot < ACCFFTB_PROFILE_SLOTS) {
+      ms[r.slot] += t, count[r.slot]++;
+    }
+  }
+  std::sort(spans.begin(), spans.end());
+  float hi = -1e30f;
+  for (auto& sp : spans) {
+    if (sp.first > hi) ms[9] += sp.second - sp.first, hi = sp.second;
+    else if (sp.second > hi) ms[9] += sp.second - hi, hi = sp.second;
+  }
+  for (auto& r : e->recs) {
     e->pool.push_back(r.a);
     e->pool.push_back(r.b);
   }

@@ -291,28 +291,33 @@ bool Plan::check_supported() {
     error = "process grid dimension exceeds kMaxSeg";
     return false;
   }
+  // every axis: a scheduled kernel, else the generic O(N^2) stage kernel (any length it can stage in shared memory; also
+  // serves r2c / c2r plans with an odd last dimension, which the scheduled kernels' N2/2-point trick cannot)
   if (g.r2c) {
-    if (g.n[2] % 2 != 0) {
-      error = "r2c plans need an even N2 (odd-length real transforms are not implemented)";
+    const bool fast = g.n[2] % 2 == 0 && be->supported(K_CONTIG_R2C, prec, g.n[2] / 2) && be->supported(K_CONTIG_C2R, prec, g.n[2] / 2);
+    if (!fast && !be->generic_ok(prec, g.n[2])) {
+      error = "no kernel for N2 = " + std::to_string(g.n[2]);
       return false;
     }
-    if (!be->supported(K_CONTIG_R2C, prec, g.n[2] / 2) || !be->supported(K_CONTIG_C2R, prec, g.n[2] / 2)) {
-      error = "no kernel schedule for N2/2 = " + std::to_string(g.n[2] / 2);
-      return false;
-    }
-  } else if (!be->supported(K_CONTIG_C2C, prec, g.n[2])) {
-    error = "no kernel schedule for N2 = " + std::to_string(g.n[2]);
+  } else if (!be->supported(K_CONTIG_C2C, prec, g.n[2]) && !be->generic_ok(prec, g.n[2])) {
+    error = "no kernel for N2 = " + std::to_string(g.n[2]);
     return false;
   }
-  if (!be->supported(K_STRIDED_C2C, prec, g.n[1])) {
-    error = "no kernel schedule for N1 = " + std::to_string(g.n[1]);
+  if (!be->supported(K_STRIDED_C2C, prec, g.n[1]) && !be->generic_ok(prec, g.n[1])) {
+    error = "no kernel for N1 = " + std::to_string(g.n[1]);
     return false;
   }
-  if (!be->supported(K_STRIDED_C2C, prec, g.n[0])) {
-    error = "no kernel schedule for N0 = " + std::to_string(g.n[0]);
+  if (!be->supported(K_STRIDED_C2C, prec, g.n[0]) && !be->generic_ok(prec, g.n[0])) {
+    error = "no kernel for N0 = " + std::to_string(g.n[0]);
     return false;
   }
   return true;
+}
+
+bool Plan::ax_supported(int axis) {
+  if (!g.r2c) return false;
+  if (axis == 2) return g.n[2] % 2 == 0 && be->supported(K_CONTIG_R2C, prec, g.n[2] / 2) && be->supported(K_CONTIG_C2R, prec, g.n[2] / 2);
+  return be->supported(K_STRIDED_R2C, prec, g.n[axis]);
 }
 
 long long Plan::buffer_bytes(const int n[3], const int np[2], const int coords[2], bool r2c, Prec prec, int nprocs) {
@@ -355,7 +360,7 @@ int Plan::prepare() {
   if (int rc = be->launch(c)) return rc;
   if (g.r2c) {
     for (int axis = 0; axis < 2; ++axis)
-      for (int mode = 0; mode < 3; ++mode) {
+      for (int mode = 0; mode < 3 && ax_supported(axis); ++mode) {
         Launch a = ax_stage(axis, mode, nullptr, nullptr);
         a.dry = true;
         if (int rc = be->launch(a)) return rc;
@@ -646,7 +651,7 @@ int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double
   return 0;
 }
 
-int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spec) {
+int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spec, bool pair_rule) {
   int rc;
   const double inv_n = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
   Launch z = fwd_z(in, false);
@@ -666,7 +671,7 @@ int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spe
     xi.desc.opAxis = ax;
     xi.desc.scale = 1.0;
     xi.desc.opOnLoad = 1;
-    xi.desc.opFullAxis = 1;
+    xi.desc.opFullAxis = pair_rule ? 0 : 1;
     if (!empty(xi) && (rc = be->launch(xi))) return rc;
     if (nprocs > 1 && (rc = bar())) return rc;
     Launch yi = inv_y();
@@ -678,7 +683,7 @@ int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spe
   return 0;
 }
 
-int Plan::execute_divergence(const void* const ins[3], void* out, void* spec) {
+int Plan::execute_divergence(const void* const ins[3], void* out, void* spec, bool pair_rule) {
   int rc;
   const double inv_n = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
   for (int ax = 0; ax < 3; ++ax) {
@@ -692,7 +697,7 @@ int Plan::execute_divergence(const void* const ins[3], void* out, void* spec) {
     x.desc.op = OP_GRAD;
     x.desc.opAxis = ax;
     x.desc.scale = inv_n;
-    x.desc.opFullAxis = 1;
+    x.desc.opFullAxis = pair_rule ? 0 : 1;
     x.desc.accumulate = ax > 0;
     if (!empty(x) && (rc = be->launch(x))) return rc;
   }
@@ -879,6 +884,10 @@ static Launch z_local(const Plan& p, bool inverse, const void* in, void* out) {
 
 int Plan::execute_r2c_axis(int axis, const void* in, void* out) {
   int rc;
+  if (!ax_supported(axis)) {
+    error = "single-axis transforms need a scheduled kernel for the axis length (accfftb_length_fast) and an even N2";
+    return -3;
+  }
   if (axis == 2) {
     Launch z = z_local(*this, false, in, out);
     return empty(z) ? 0 : be->launch(z);
@@ -898,6 +907,10 @@ int Plan::execute_r2c_axis(int axis, const void* in, void* out) {
 
 int Plan::execute_c2r_axis(int axis, const void* in, void* out) {
   int rc;
+  if (!ax_supported(axis)) {
+    error = "single-axis transforms need a scheduled kernel for the axis length (accfftb_length_fast) and an even N2";
+    return -3;
+  }
   if (axis == 2) {
     Launch z = z_local(*this, true, in, out);
     return empty(z) ? 0 : be->launch(z);
@@ -973,6 +986,9 @@ int Plan::execute_deriv_axis(int axis, const void* in, void* out, bool accumulat
 }
 
 int Plan::execute_grad_axes(const void* in, void* const outs[3], int comps, void* spec) {
+  // an axis length without per-axis kernels: the full 3-D scheme with the per-axis scheme's Nyquist rule is the same operator
+  for (int ax = 0; ax < 3; ++ax)
+    if (ax < 2 && (comps & (1 << ax)) && !ax_supported(ax)) return execute_grad(in, outs, comps, spec, true);   // (z is always local)
   for (int ax = 0; ax < 3; ++ax) {
     if (!(comps & (1 << ax))) continue;
     if (int rc = execute_deriv_axis(ax, in, outs[ax], false, spec)) return rc;
@@ -981,6 +997,8 @@ int Plan::execute_grad_axes(const void* in, void* const outs[3], int comps, void
 }
 
 int Plan::execute_divergence_axes(const void* const ins[3], void* out, void* spec) {
+  for (int ax = 0; ax < 2; ++ax)
+    if (!ax_supported(ax)) return execute_divergence(ins, out, spec, true);
   // z first: its fused kernel runs few warps per SM and would expose the latency of the read-modify-write that
   // accumulation needs (measured: 3.11 ms with z last vs 2.5 ms at 512^3 double); the strided x / y kernels hide it
   const int order[3] = {2, 0, 1};

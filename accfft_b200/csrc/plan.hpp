@@ -16,7 +16,9 @@ namespace accfft_b200 {
 // implements it with host memory and a fiber emulator (test infrastructure only).
 struct Backend {
   virtual ~Backend() {}
-  virtual bool supported(Kind kind, Prec prec, int fftN) = 0;
+  virtual bool supported(Kind kind, Prec prec, int fftN) = 0;   // a scheduled (fast) kernel exists for this complex length
+  // the generic O(N^2) stage kernel can run a 3-D transform axis of this (real or complex) length (generic_dft.cu)
+  virtual bool generic_ok(Prec, int /*N*/) { return false; }
   virtual const void* twiddle(Prec prec, int tableN) = 0;   // W_tableN[k], k < tableN
   virtual int launch(const Launch& l) = 0;                   // enqueue on the plan's stream; 0 = ok
   virtual int barrier() = 0;                                 // all ranks of the comm, stream ordered
@@ -116,6 +118,8 @@ struct Plan {
   int execute_divergence_axes(const void* const ins[3], void* out, void* spec);
 
   bool check_supported();
+  // do the fused per-axis kernels (single-axis real transforms, per-axis derivative) exist for this axis?
+  bool ax_supported(int axis);
   // Load and configure every kernel the plan can launch (CUDA loads kernels lazily, and a first-use load may
   // synchronise the context -- which must not happen while another rank's barrier kernel is spinning).
   int prepare();
@@ -139,10 +143,11 @@ struct Plan {
   int execute_spectral(const void* in, void* out, int op, void* spec, double opA = 0.0, double opB = 0.0);
   // grad (src/operators_gpu.txx:72-278): one forward into `spec` (normalised), then per selected component
   // an inverse whose X stage multiplies by i*k_axis on load.  comps: bit 0 = x, bit 1 = y, bit 2 = z.
-  int execute_grad(const void* in, void* const outs[3], int comps, void* spec);
+  // pair_rule: zero the mode pair +-floor(N/2) like the per-axis scheme does (used when that scheme has no kernel for a length)
+  int execute_grad(const void* in, void* const outs[3], int comps, void* spec, bool pair_rule = false);
   // divergence (src/operators_gpu.txx:336-553): three forwards whose X stage multiplies by i*k_axis and
   // accumulates into `spec`, then one inverse.
-  int execute_divergence(const void* const ins[3], void* out, void* spec);
+  int execute_divergence(const void* const ins[3], void* out, void* spec, bool pair_rule = false);
 };
 
 unsigned blk_magic(int blk);

@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+# plan stream + copy lanes + the e2e copy streams + NCCL's own: keep every stream on its own hardware queue (default: 8)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -164,6 +167,169 @@ def run_reference(args):
     return 0
 
 
+
+# ---------------------------------------------------------------------------------------------------
+# parity inside the bench (N > 1): every rank checks ITS blocks against the oracle (tests/ holds the full suite; this
+# puts multi-GPU forward-spectrum / operator parity on real GPUs into the driver-visible record)
+# ---------------------------------------------------------------------------------------------------
+PENCIL = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}     # the pencil grids BASELINE.json names (2x4 at 8 GPUs)
+PARITY_SIZES = [(128, 96, 160), (5, 6, 6)]               # uneven pencils; (5, 6, 6) leaves ranks short or empty
+
+
+def parity_case(acc, orc, torch, dist, dev, n, dims, world, rank):
+    """-> {check: max over ranks of the relative L2 error vs the oracle} for one grid; all ranks must call"""
+    import numpy as np
+    comm = acc.accfft_create_comm(list(dims), rank=rank, nprocs=world)
+    p = acc.Plan(n, comm, r2c=True, single=False, flags=acc.ACCFFT_ESTIMATE)
+    x = orc.synthetic_real(n, 5)
+    X = orc.forward_r2c(x)
+    loc = orc.local_input(x, n, dims, comm.coords)
+    xd = torch.from_numpy(np.ascontiguousarray(loc)).to(dev) if loc.size else torch.zeros(2, dtype=torch.float64, device=dev)
+    out = torch.zeros(max(p.alloc_max // 8, 2), dtype=torch.float64, device=dev)
+    back = torch.zeros_like(xd)
+    errs = {"forward": 0.0, "round_trip": 0.0, "laplace": 0.0, "grad": 0.0}
+    for _ in range(2):
+        p.execute_r2c(xd, out)
+        p.execute_c2r(out, back)
+    osz = p.osize
+    cnt = osz[0] * osz[1] * osz[2]
+    if cnt:
+        got = out.cpu().numpy().view(np.complex128)[:cnt].reshape(osz)
+        errs["forward"] = orc.rel_l2(got, orc.local_output(X, n, dims, comm.coords, r2c=True))
+    la = torch.zeros_like(xd)
+    g = [torch.zeros_like(xd) for _ in range(3)]
+    p.laplace(la, xd)
+    p.grad(g[0], g[1], g[2], xd)
+    if loc.size:
+        errs["round_trip"] = orc.rel_l2(back.cpu().numpy().reshape(loc.shape) / x.size, loc)
+        errs["laplace"] = orc.rel_l2(la.cpu().numpy().reshape(loc.shape), orc.local_input(orc.laplace(x), n, dims, comm.coords))
+        errs["grad"] = max(orc.rel_l2(g[ax].cpu().numpy().reshape(loc.shape), orc.local_input(orc.grad(x, ax), n, dims, comm.coords))
+                           for ax in range(3))
+    mode = p.exchange_mode()["mode"]
+    p.destroy()
+    keys = sorted(errs)
+    t = torch.tensor([errs[k] for k in keys], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {k: float(v) for k, v in zip(keys, t.tolist())}, mode
+
+
+def run_parity(acc, torch, dist, dev, world, rank, run_dims):
+    from oracle import accfft_oracle as orc
+    grids = [tuple(run_dims)]
+    if tuple(PENCIL.get(world, run_dims)) not in grids:
+        grids.append(tuple(PENCIL[world]))
+    out, worst = {}, 0.0
+    for dims in grids:
+        for n in PARITY_SIZES:
+            errs, mode = parity_case(acc, orc, torch, dist, dev, n, dims, world, rank)
+            out["%dx%dx%d on %dx%d (%s)" % (n[0], n[1], n[2], dims[0], dims[1], mode)] = errs
+            worst = max(worst, max(errs.values()))
+    return out, worst
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3-5 (the non-headline configurations), time-boxed: a few iterations each, on the pencil grid
+# BASELINE names and on the slab grid; each with its own round-trip guard and roofline fraction
+# ---------------------------------------------------------------------------------------------------
+def time_plan(torch, dist, dev, world, fn, iters, warm=2):
+    st = torch.cuda.current_stream()
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(iters):
+        fn()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def config_entry(acc, torch, dist, dev, world, rank, name, n, dims, r2c, single, peak, operators=False, iters=5):
+    """one BASELINE config on one grid: round trip ms / TFLOP/s / fraction of max(HBM, NVLink) roofline (+ operators)"""
+    comm = acc.accfft_create_comm(list(dims), rank=rank, nprocs=world)
+    p = acc.Plan(n, comm, r2c=r2c, single=single)
+    rdt = torch.float32 if single else torch.float64
+    es = 4 if single else 8
+    isz, osz = p.isize, p.osize
+    cnt = isz[0] * isz[1] * isz[2] * (1 if r2c else 2)
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+    x = torch.rand(max(cnt, 2), dtype=rdt, device=dev, generator=gen) * 2 - 1
+    out = torch.zeros(max(p.alloc_max // es, 2), dtype=rdt, device=dev)
+    back = torch.zeros_like(x)
+    p.set_stream(torch.cuda.current_stream().cuda_stream)
+    p.set_blocking(False)
+
+    def step():
+        if r2c:
+            p.execute_r2c(x, out)
+            p.execute_c2r(out, back)
+        else:
+            p.execute_c2c(acc.ACCFFT_FORWARD, x, out)
+            p.execute_c2c(acc.ACCFFT_BACKWARD, out, back)
+
+    ms = time_plan(torch, dist, dev, world, step, iters)
+    N = n[0] * n[1] * n[2]
+    err = float(torch.linalg.vector_norm(back[:cnt] / N - x[:cnt]) / torch.linalg.vector_norm(x[:cnt])) if cnt else 0.0
+    t = torch.tensor([err], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    err = float(t.item())
+    # roofline of this rank's share: every axis pass reads and writes its array once; the exchanged part crosses NVLink
+    n2c = n[2] // 2 + 1 if r2c else n[2]
+    cs = 2 * es
+    R = isz[0] * isz[1] * isz[2] * (es if r2c else cs)
+    C0 = isz[0] * isz[1] * n2c * cs
+    C1 = isz[0] * n[1] * osz[2] * cs
+    C2 = n[0] * osz[1] * osz[2] * cs
+    hbm = 2 * (R + C0 + 2 * C1 + 2 * C2)
+    P0, P1 = dims
+    nvl = 2 * (C0 * (P1 - 1) / P1 + C1 * (P0 - 1) / P0)
+    t_roof = max(hbm / (peak * 1e9), nvl / (NVLINK_GBS * 1e9)) * 1e3
+    e = {"grid": "%dx%d" % dims, "exchange": p.exchange_mode()["mode"], "ms": ms, "tflops": 2 * flops_per_transform(n) / (ms * 1e-3) / 1e12,
+         "t_roof_ms": t_roof, "frac_of_roofline": t_roof / ms, "round_trip_rel_l2": err,
+         "tolerance": 1e-5 if single else 1e-12, "ok": err <= (1e-5 if single else 1e-12)}
+    if operators and r2c:
+        la = torch.zeros_like(x)
+        g = [torch.zeros_like(x) for _ in range(3)]
+        e["laplace_ms"] = time_plan(torch, dist, dev, world, lambda: p.laplace(la, x), iters)
+        e["grad_ms"] = time_plan(torch, dist, dev, world, lambda: p.grad(g[0], g[1], g[2], x), iters)
+        # laplace = one forward + one inverse with the symbol fused into the X stage: same roofline as the round trip;
+        # grad (per-axis scheme): three single-axis derivative passes, each reads and writes the real field once (+ exchanges)
+        e["laplace_frac_of_roofline"] = t_roof / e["laplace_ms"]
+    p.destroy()
+    del x, out, back
+    torch.cuda.empty_cache()
+    return e
+
+
+def run_configs(acc, torch, dist, dev, world, rank, peak):
+    slab, pencil = (world, 1), tuple(PENCIL.get(world, (world, 1)))
+    grids = [pencil] + ([slab] if slab != pencil else [])
+    specs = [("config3: 512^3 double c2c forward + backward", (512, 512, 512), False, False, False),
+             ("config4: 1024^3 single r2c + c2r, fused laplace / grad operators", (1024, 1024, 1024), True, True, True),
+             ("config5: 768x768x384 double r2c + c2r (mixed radix 2/3, uneven pencils)", (768, 768, 384), True, False, False)]
+    out = {}
+    for name, n, r2c, single, ops in specs:
+        out[name] = []
+        for dims in grids:
+            try:
+                out[name].append(config_entry(acc, torch, dist, dev, world, rank, name, n, dims, r2c, single, peak, operators=ops))
+            except Exception as ex:   # a config that does not fit (memory) is reported, not fatal for the headline line
+                out[name].append({"grid": "%dx%d" % dims, "error": repr(ex)[:200]})
+                torch.cuda.empty_cache()
+    return out
+
+
 METRIC = "3D r2c+c2r GFLOP/s (5N*log2N per transform) at 512^3 double"
 
 
@@ -178,6 +344,8 @@ def main():
     ap.add_argument("--grid", default=None, help="process grid P0xP1 (default: see GRIDS)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity block (N > 1)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3-5 block (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -205,6 +373,15 @@ def main():
         dims = [int(v) for v in args.grid.lower().split("x")]
         if dims[0] * dims[1] != world:
             raise SystemExit("--grid %s does not match %d ranks" % (args.grid, world))
+    peak, peak_src = measured_peaks()
+    # ---- multi-GPU parity, BEFORE anything is timed: no value is printed if a block of any rank is off ----------------
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity, worst = run_parity(acc, torch, dist, dev, world, rank, dims)
+        if not worst <= 1e-12:
+            raise SystemExit("multi-GPU parity failed (worst relative L2 %.3e > 1e-12): %s" % (worst, json.dumps(parity)))
+        parity = {"tolerance": 1e-12, "worst": worst, "checks": "forward spectrum / round trip / laplace / grad, per rank vs the "
+                  "oracle, max over ranks", "cases": parity}
     comm = acc.accfft_create_comm(dims, rank=rank, nprocs=world)
     plan = acc.accfft_plan_dft_3d_r2c_gpu(n, comm)
     isz, osz = plan.isize, plan.osize
@@ -243,6 +420,7 @@ def main():
     plan.profile_read()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = plan.launch_count
+    copies0 = plan.copy_count
     sync_all()
     with torch.cuda.stream(stream):
         ev0.record(stream)
@@ -252,6 +430,7 @@ def main():
     sync_all()
     ms = ev0.elapsed_time(ev1)
     launches = plan.launch_count - launches0
+    copies = plan.copy_count - copies0
     prof = plan.profile_read()
     plan.set_profiling(False)
     if world > 1:
@@ -334,10 +513,25 @@ def main():
     algo = {"fwd_z": R + C0, "fwd_y": C1 + C1, "fwd_x": C2 + C2, "inv_x": C2 + C2, "inv_y": C1 + C1, "inv_z": C0 + R}
     if world > 1:      # the stage that feeds an exchange writes the NEXT layout's bytes (same totals on even grids)
         algo["fwd_z"] = R + C0
-    peak, peak_src = measured_peaks()
-    # bytes each stage stores into OTHER ranks' buffers over NVLink (the exchange is fused into the stage's stores)
+    # bytes that leave this GPU over NVLink with each exchanging stage (peer stores fused into the stage, or copy-engine
+    # transfers of what the stage packed)
     nvl = {"fwd_z": C0 * (dims[1] - 1) / dims[1], "fwd_y": C1 * (dims[0] - 1) / dims[0],
            "inv_x": C2 * (dims[0] - 1) / dims[0], "inv_y": C0 * (dims[1] - 1) / dims[1]}
+    xmode = plan.exchange_mode()
+    exchange = dict(xmode)
+    if xmode["mode"] == "copy_engine":
+        # the exchanging stages pack into a local staging buffer (HBM-bound kernels); copy engines move it over NVLink
+        # while the next chunk computes: the link traffic belongs to the transfers, not to a kernel
+        nvl_step = sum(nvl.values())
+        cms, ccnt = prof.get("ce_copy", (0.0, 0))
+        exchange.update({"nvlink_out_bytes_per_step": int(nvl_step), "transfers_per_step": ccnt / args.steps,
+                         "transfer_busy_ms_per_step": cms / args.steps,
+                         "nvlink_out_gbs": (nvl_step / (cms / args.steps * 1e-3) / 1e9) if cms else None,
+                         "nvlink_peak_gbs": NVLINK_GBS,
+                         "nvlink_frac": (nvl_step / (cms / args.steps * 1e-3) / 1e9 / NVLINK_GBS) if cms else None,
+                         "overlap": "transfer of chunk c runs on copy lanes while chunk c+1 computes; busy time = union of "
+                                    "the transfer intervals (CUDA events on the copy streams)"})
+        nvl = {}
     stages = {}
     for k, (tms, cnt) in prof.items():
         if cnt:
@@ -359,12 +553,17 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": stages[dom]["gbs"] / peak, "traffic": traffic,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, one --set full "
+                                  "capture (profiles/traffic.json); not re-measured in this run" if traffic else None,
                 "algo_bytes_per_launch": algo[dom] / stages[dom]["launches_per_step"],
                 "ms_per_launch": stages[dom]["ms"], "peak_source": peak_src}
-    if "nvlink_out_gbs" in stages[dom]:   # the dominant kernel stores to peers: its ceiling is the link, not HBM
-        roofline.update({"nvlink_out_gbs": stages[dom]["nvlink_out_gbs"], "nvlink_peak_gbs": NVLINK_GBS,
-                         "nvlink_frac": stages[dom]["nvlink_out_gbs"] / NVLINK_GBS,
-                         "note": "this stage's stores cross NVLink (exchange fused into the FFT kernel): NVLink-bound, see nvlink_frac"})
+    if "nvlink_out_gbs" in stages[dom]:
+        # the dominant kernel stores to peers (exchange fused into the FFT kernel): its ceiling is the link, not HBM
+        roofline.update({"bound": "nvlink", "achieved": stages[dom]["nvlink_out_gbs"], "peak": NVLINK_GBS,
+                         "frac": stages[dom]["nvlink_out_gbs"] / NVLINK_GBS, "hbm_gbs": stages[dom]["gbs"],
+                         "hbm_frac": stages[dom]["gbs"] / peak,
+                         "peak_source": "measured peer-copy bandwidth per direction (B200_PROFILING.md)",
+                         "note": "achieved = bytes this stage stores into peers' buffers / its duration"})
     # whole-step view: sum of algorithmic bytes of the six passes vs the step time
     total_algo = sum(algo.values())
     # roofline of the whole step: perfect-overlap model  T = max(HBM bytes / HBM peak, NVLink bytes out / link peak)
@@ -396,6 +595,18 @@ def main():
                         "sample": "best of %d full %d^3 double r2c+c2r round trip(s), scipy.fft pocketfft workers=%d "
                                   "(stand-in for FFTW+MPI, which cannot be built here)" % (reps, args.n, cores)}
 
+    # ---- BASELINE configs 3-5 (N > 1): after the headline plan is gone, so that their buffers fit next to nothing ----
+    stage_kernels = plan.stage_kernels()
+    plan.destroy()
+    del x, out, back
+    torch.cuda.empty_cache()
+    configs = None
+    if world > 1 and not args.no_configs and args.n == 512:
+        configs = run_configs(acc, torch, dist, dev, world, rank, peak)
+        bad = [(k, c) for k, v in configs.items() for c in v if c.get("ok") is False]
+        if bad:
+            raise SystemExit("a BASELINE config failed its round-trip guard: %s" % json.dumps(bad))
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -407,10 +618,10 @@ def main():
                        ((R + 2 * C0) / 1e9), "round_trip_rel_l2": rt_err},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "stages": stages, "step_roofline": step_roof,
-            "stage_kernels": plan.stage_kernels(),
+            "stage_kernels": stage_kernels, "exchange": exchange, "gpu_copies": int(copies),
+            "parity": parity, "configs": configs,
         }
         print(json.dumps(line), flush=True)
-    plan.destroy()
     if world > 1:
         dist.destroy_process_group()
     return 0

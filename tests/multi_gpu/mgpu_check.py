@@ -3,6 +3,7 @@
 Compares every rank's block with the numpy oracle (rank 0 generates the global field from a seed; every rank
 regenerates it locally -- no data collective is needed for the check)."""
 import os, sys, json
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch

@@ -154,8 +154,10 @@ def test_create_comm_overwrites_bad_dims(nprocs, dims_in, dims_out):
 def test_supported_lengths():
     for n in (2, 3, 4, 5, 6, 8, 12, 16, 27, 64, 96, 125, 128, 192, 216, 250, 256, 384, 500, 512, 768, 1000, 1024, 1728, 2000, 2048,
               7, 11, 13, 14, 49, 98, 448, 896, 1792, 44, 52, 4096):
-        assert acc.length_supported(n), n
-    for n in (81, 625, 1023, 17, 77, 343, 8192):
+        assert acc.length_fast(n) and acc.length_supported(n), n
+    for n in (81, 625, 1023, 17, 77, 343, 7168):     # no compiled schedule: planned through the generic O(n^2) stage kernel
+        assert not acc.length_fast(n) and acc.length_supported(n), n
+    for n in (0, -4, 7169, 8192):
         assert not acc.length_supported(n), n
 
 

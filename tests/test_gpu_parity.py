@@ -69,7 +69,7 @@ SIZES = [(8, 8, 8), (16, 12, 20), (2, 2, 2), (4, 6, 10), (5, 3, 8), (32, 48, 64)
          (125, 27, 250), (4, 6, 2000), (1000, 8, 12), (12, 1728, 8), (500, 6, 54), (8, 1500, 10), (6, 10, 1728), (216, 432, 108),
          (135, 270, 6), (375, 4, 540), (8, 675, 750), (1080, 6, 4), (4, 1125, 6), (6, 4, 1350), (864, 4, 6), (450, 6, 4),
          # prime radices 7 / 11 / 13, the composite 14, and 4096-long axes (three radix-16 passes, 256 threads per column)
-         (7, 14, 22), (49, 13, 26), (28, 44, 98), (448, 6, 56), (6, 1792, 8), (4, 6, 1456), (12, 10, 14),
+         (7, 14, 22), (49, 13, 26), (28, 44, 98), (448, 6, 56), (6, 1792, 8), (4, 6, 896), (12, 10, 14),
          (4096, 4, 6), (6, 4096, 4), (4, 6, 8192)]
 
 
@@ -90,6 +90,49 @@ def test_r2c_forward_and_c2r_against_oracle(cuda_device, n, single, stage_kernel
     assert orc.rel_l2(back.cpu().numpy(), x * x.size) <= TOL[single]
     # c2r must not clobber its input here (deliberate fix of src/accfft_gpu.cpp:544-545)
     assert np.array_equal(Xd.cpu().numpy(), X.astype(dtypes(single)[1]))
+    p.destroy()
+
+
+GENERIC_SIZES = [(8, 8, 9), (17, 6, 10), (6, 19, 8), (4, 6, 46), (5, 7, 23), (31, 29, 37), (12, 34, 81), (3, 1021, 4), (6, 5, 7)]
+
+
+@pytest.mark.parametrize("n", GENERIC_SIZES)
+@pytest.mark.parametrize("single", [False, True])
+def test_any_length_plans_generic_kernel(cuda_device, n, single):
+    """lengths without a compiled schedule (primes >= 17, 81, ...) and odd N2 in r2c plans: the generic O(N^2) stage kernel
+    (csrc/generic_dft.cu) -- the reference accepts any length (cuFFT, src/accfft_gpu.cpp:173-253)"""
+    torch = torch_mod()
+    rdt, cdt = dtypes(single)
+    x = orc.synthetic_real(n, 3)
+    p = make_plan(n, True, single)
+    xd = to_dev(x.astype(rdt), cuda_device)
+    out = alloc_out(p, single, cuda_device)
+    p.execute_r2c(xd, out)
+    assert orc.rel_l2(spectrum(out, n, single), orc.forward_r2c(x)) <= TOL[single]
+    back = torch.zeros_like(xd)
+    p.execute_c2r(out, back)
+    assert orc.rel_l2(back.cpu().numpy() / x.size, x) <= TOL[single]
+    tol = 1e-12 if not single else 2e-5
+    la = torch.zeros_like(xd)
+    p.laplace(la, xd)
+    assert orc.rel_l2(la.cpu().numpy(), orc.laplace(x)) <= tol
+    g = [torch.zeros_like(xd) for _ in range(3)]
+    p.grad(g[0], g[1], g[2], xd)          # per-axis scheme where the axis has kernels, the 3-D scheme (same operator) elsewhere
+    for ax in range(3):
+        assert orc.rel_l2(g[ax].cpu().numpy(), orc.grad(x, ax)) <= tol, ax
+    dv = torch.zeros_like(xd)
+    p.divergence(dv, g[0], g[1], g[2])
+    assert orc.rel_l2(dv.cpu().numpy(), orc.divergence(*[orc.grad(x, ax) for ax in range(3)])) <= 10 * tol
+    p.destroy()
+    z = orc.synthetic_complex(n, 4)
+    p = make_plan(n, False, single)
+    zd = torch.view_as_real(to_dev(z.astype(cdt), cuda_device)).contiguous()
+    out = alloc_out(p, single, cuda_device)
+    p.execute_c2c(acc.ACCFFT_FORWARD, zd, out)
+    assert orc.rel_l2(spectrum(out, n, single, r2c=False), orc.forward_c2c(z)) <= TOL[single]
+    back = torch.zeros_like(zd)
+    p.execute_c2c(acc.ACCFFT_BACKWARD, out, back)
+    assert orc.rel_l2(back.cpu().numpy().ravel().view(cdt).reshape(n) / z.size, z) <= TOL[single]
     p.destroy()
 
 
@@ -458,10 +501,13 @@ def test_full_size_c2c_roundtrip_512(cuda_device):
 def test_error_behaviour(cuda_device):
     torch = torch_mod()
     comm = acc.Comm(0, 1, (1, 1))
-    with pytest.raises(acc.AccfftError):     # odd N2 for r2c
-        acc.accfft_plan_dft_3d_r2c_gpu((8, 8, 9), comm)
-    with pytest.raises(acc.AccfftError):     # no schedule for 17
-        acc.accfft_plan_dft_3d_c2c_gpu((17, 8, 8), comm)
+    with pytest.raises(acc.AccfftError):     # beyond what even the generic stage kernel can stage
+        acc.accfft_plan_dft_3d_c2c_gpu((9000, 8, 8), comm)
+    q = acc.accfft_plan_dft_3d_r2c_gpu((8, 17, 8), comm)     # plans (generic kernel along Y) ...
+    xq = torch.zeros(8 * 17 * 8, dtype=torch.float64, device=cuda_device)
+    with pytest.raises(acc.AccfftError):     # ... but the single-axis executes exist for scheduled lengths only
+        q.execute_r2c_axis(1, xq, alloc_out(q, False, cuda_device))
+    q.destroy()
     p = acc.accfft_plan_dft_3d_r2c_gpu((8, 8, 8), comm)
     x = torch.zeros(8 * 8 * 8, dtype=torch.float64, device=cuda_device)
     out = alloc_out(p, False, cuda_device)
