@@ -116,6 +116,103 @@ __global__ void __launch_bounds__(32) k_barrier(const __grid_constant__ BarrierD
   __threadfence_system();
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// TMA push kernel: the transfer engine of the slab exchange (Plan::forward_slab_ce / inverse_slab_ce).  Moves a 2-D block
+// (`height` rows of `width` bytes) from the local staging buffer into a peer's exchange buffer over NVLink with a handful of
+// CTAs: one elected thread per CTA streams tiles  global --cp.async.bulk--> shared --cp.async.bulk--> peer global  through a
+// ring of shared-memory buffers (loads run NBUF-1 tiles ahead, completing on mbarriers; stores are bulk groups).  The TMA
+// unit keeps hundreds of KB per SM in flight, so ~16 SMs fill the link while the other ~130 run the next chunk's FFT stages
+// at HBM speed -- measured on this pool, copy engines (cudaMemcpyAsync) reach only ~500 GB/s per direction when both
+// directions and a concurrent HBM-bound kernel are active, SM / TMA stores 650-680 (profiles/ce_vs_push_r2.txt).
+// All addresses, pitches and the width are multiples of 16 bytes (the caller falls back to the copy engine otherwise).
+// ---------------------------------------------------------------------------------------------------
+struct PushDesc {
+  const char* src;
+  char* dst;
+  unsigned long long spitch, dpitch, width, height;
+  unsigned tile;   // bytes per tile (multiple of 16, <= kPushTile)
+};
+constexpr unsigned kPushTile = 32 * 1024;
+constexpr int kPushBufs = 6;
+constexpr int kPushSmem = kPushTile * kPushBufs + 128;
+
+__device__ __forceinline__ void push_mbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)));
+}
+__device__ __forceinline__ void push_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void push_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "PW_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra PD_%=;\n"
+      " bra PW_%=;\n"
+      "PD_%=:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void push_store(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(32) k_push(const __grid_constant__ PushDesc d) {
+  extern __shared__ unsigned char push_smem_raw[];
+  unsigned char* base = (unsigned char*)(((uintptr_t)push_smem_raw + 127) & ~(uintptr_t)127);
+  unsigned long long* bars = (unsigned long long*)(base + (size_t)kPushTile * kPushBufs);
+  if (threadIdx.x != 0) return;
+  const unsigned long long tiles_per_row = (d.width + d.tile - 1) / d.tile;
+  const unsigned long long ntiles = tiles_per_row * d.height;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const unsigned long long first = blockIdx.x, step = gridDim.x;
+  if (first >= ntiles) return;
+  const unsigned long long nmine = (ntiles - first + step - 1) / step;
+  for (int b = 0; b < kPushBufs; ++b) push_mbar_init(&bars[b]);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  auto geom = [&](unsigned long long i, const char*& src, char*& dst, unsigned& bytes) {
+    const unsigned long long t = first + i * step;
+    const unsigned long long row = t / tiles_per_row, col = (t % tiles_per_row) * d.tile;
+    const unsigned long long left = d.width - col;
+    bytes = (unsigned)(left < d.tile ? left : d.tile);
+    src = d.src + row * d.spitch + col;
+    dst = d.dst + row * d.dpitch + col;
+  };
+  auto load = [&](unsigned long long i) {
+    const char* src;
+    char* dst;
+    unsigned bytes;
+    geom(i, src, dst, bytes);
+    push_load(base + (size_t)(i % kPushBufs) * kPushTile, src, bytes, &bars[i % kPushBufs]);
+  };
+  for (unsigned long long j = 0; j + 1 < (unsigned long long)kPushBufs && j < nmine; ++j) load(j);
+  for (unsigned long long i = 0; i < nmine; ++i) {
+    if (i + kPushBufs - 1 < nmine) {
+      // the buffer of tile i + NBUF - 1 last held tile i - 1: its store must have read it (at most store i-1's successor pending)
+      if (i > 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      load(i + kPushBufs - 1);
+    }
+    const char* src;
+    char* dst;
+    unsigned bytes;
+    geom(i, src, dst, bytes);
+    push_wait(&bars[i % kPushBufs], (unsigned)((i / kPushBufs) & 1));
+    push_store(dst, base + (size_t)(i % kPushBufs) * kPushTile, bytes);
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Stage without a transform (partial-axis executes, xyz != 111): the same descriptor as the FFT stage, but every
 // element just moves to where the next layout wants it.  The reference does this with its transposes alone
@@ -192,6 +289,7 @@ struct Engine {
   static constexpr int kMaxCopyLanes = 8;
   int ce_chunks = 0;           // ACCFFT_B200_CE: chunks per exchanging stage (0: direct peer stores instead)
   int ce_lanes = 0;            // ACCFFT_B200_CE_LANES: copy streams (copies to different peers overlap)
+  int push_ctas = 0;           // ACCFFT_B200_PUSH: CTAs of the TMA push kernel per transfer (0: copy engines / cudaMemcpyAsync)
   cudaStream_t copy_streams[kMaxCopyLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* stage_buf = nullptr;   // local staging buffer of the exchanging stage (one exchange buffer long)
   int variant_local[ACCFFTB_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // tuned kernel variant of a stage when it stores locally
@@ -345,6 +443,26 @@ int CudaBackend::copy2d(int lane, void* dst, size_t dpitch, const void* src, siz
   if (!width || !height) return 0;
   LaneScope lane_scope(e, lane);
   ScopedProfile pf(e, 9);
+  const bool aligned = ((((uintptr_t)dst | (uintptr_t)src | width) & 15) == 0) && (height == 1 || ((dpitch | spitch) & 15) == 0);
+  if (e->push_ctas > 0 && aligned) {
+    // TMA push kernel on a few SMs (see k_push)
+    PushDesc pd;
+    pd.src = (const char*)src;
+    pd.dst = (char*)dst;
+    pd.spitch = spitch;
+    pd.dpitch = dpitch;
+    pd.width = width;
+    pd.height = height;
+    pd.tile = kPushTile;
+    const unsigned long long ntiles = ((width + kPushTile - 1) / kPushTile) * height;
+    const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)e->push_ctas);
+    k_push<<<grid, 32, kPushSmem, e->stream>>>(pd);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return cuda_fail(err, "push kernel launch");
+    e->launches++;
+    e->copies++;
+    return 0;
+  }
   if (height == 1) CU(cudaMemcpyAsync(dst, src, width, cudaMemcpyDeviceToDevice, e->stream));
   else CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToDevice, e->stream));
   e->copies++;
@@ -770,14 +888,26 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
     }
     // copy-engine exchange: slab grids only (one exchange per transform, both of its ends local)
     if (pl.nprocs > 1 && c_dims[1] == 1) {
-      e->ce_chunks = 4;
-      e->ce_lanes = std::min(pl.nprocs - 1, 4);
+      e->ce_chunks = 0;   // default: direct peer stores (see DESIGN.md section 5 for the measurements behind this choice)
+      e->ce_lanes = 4;
       if (const char* m = getenv("ACCFFT_B200_CE")) e->ce_chunks = atoi(m);
       if (const char* m = getenv("ACCFFT_B200_CE_LANES")) e->ce_lanes = std::max(1, std::min(atoi(m), (int)Engine::kMaxCopyLanes));
+      e->push_ctas = 16;
+      if (const char* m = getenv("ACCFFT_B200_PUSH")) e->push_ctas = std::max(0, atoi(m));
+      if (e->push_ctas > 0) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, k_push) != cudaSuccess ||
+            cudaFuncSetAttribute(k_push, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushSmem) != cudaSuccess) {
+          cudaGetLastError();
+          e->push_ctas = 0;
+        }
+      }
       if (e->ce_chunks > 0) {
         cudaError_t ce = cudaMalloc((void**)&e->stage_buf, e->bufsz);
-        for (int l = 0; l < e->ce_lanes && ce == cudaSuccess; ++l)
-          ce = cudaStreamCreateWithFlags(&e->copy_streams[l], cudaStreamNonBlocking);
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // hi = greatest priority (numerically least)
+        for (int l = 0; l < e->ce_lanes && ce == cudaSuccess; ++l)   // highest priority: push CTAs take SMs as compute CTAs retire
+          ce = cudaStreamCreateWithPriority(&e->copy_streams[l], cudaStreamNonBlocking, prio_hi);
         if (ce != cudaSuccess) {   // no room / no streams: fall back to the direct peer-store path
           cudaGetLastError();
           if (e->stage_buf) cudaFree(e->stage_buf), e->stage_buf = nullptr;
