@@ -227,18 +227,38 @@ class Plan:
         L = lib()
         self._h = L.accfftb_plan_create(_i3(n), _i2(comm.c_dims), comm.rank, _R2C if r2c else _C2C,
                                         _FLOAT if single else _DOUBLE, flags)
-        if not self._h:
+        err = None if self._h else "plan creation failed: " + _err()
+        # plan creation is collective: agree on the outcome before anybody waits for anybody's IPC blob (the C++ layer does
+        # the same with an MPI_Allreduce(MIN), csrc/accfft_gpu_api.cpp), so that a failure on one rank raises on ALL ranks
+        # instead of leaving the others blocked in the all-gather below
+        collective = comm.nprocs > 1 and wire
+        if collective:
+            oks = comm.all_gather_bytes(b"\x01" if err is None else b"\x00")
+            if err is None and any(o != b"\x01" for o in oks):
+                err = "plan creation failed on rank(s) %s" % [i for i, o in enumerate(oks) if o != b"\x01"]
+        if err is not None:
+            if self._h:
+                L.accfftb_plan_destroy(self._h)
+                self._h = None
             # the reference prints and returns NULL (src/accfft_gpu.cpp:187-191); raise with the message instead
-            raise AccfftError("plan creation failed: " + _err())
+            raise AccfftError(err)
         sz = (accfft_local_size_dft_r2c_gpuf if single else accfft_local_size_dft_r2c_gpu) if r2c else \
              (accfft_local_size_dft_c2c_gpuf if single else accfft_local_size_dft_c2c_gpu)
         self.alloc_max, self.isize, self.istart, self.osize, self.ostart = sz(n, comm)
-        if comm.nprocs > 1 and wire:
+        if collective:
             blob = ctypes.create_string_buffer(_BLOB)
-            _check(L.accfftb_plan_ipc_export(self._h, blob), "accfftb_plan_ipc_export")
+            rc = L.accfftb_plan_ipc_export(self._h, blob)
             blobs = b"".join(comm.all_gather_bytes(blob.raw))
-            buf = ctypes.create_string_buffer(blobs, len(blobs))
-            _check(L.accfftb_plan_ipc_import(self._h, buf, comm.nprocs), "accfftb_plan_ipc_import")
+            if rc == 0:
+                buf = ctypes.create_string_buffer(blobs, len(blobs))
+                rc = L.accfftb_plan_ipc_import(self._h, buf, comm.nprocs)
+            msg = _err() if rc else ""
+            oks = comm.all_gather_bytes(b"\x01" if rc == 0 else b"\x00")
+            if any(o != b"\x01" for o in oks):
+                L.accfftb_plan_destroy(self._h)
+                self._h = None
+                raise AccfftError("wiring the exchange buffers failed on rank(s) %s%s" %
+                                  ([i for i, o in enumerate(oks) if o != b"\x01"], (": " + msg) if msg else ""))
             comm.barrier()
 
     # ---- configuration -------------------------------------------------------------------------
@@ -418,9 +438,16 @@ class Plan:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None) and self.comm.nprocs == 1:
-                lib().accfftb_plan_destroy(self._h)
-                self._h = None
+            if getattr(self, "_h", None):
+                if self.comm.nprocs == 1:
+                    lib().accfftb_plan_destroy(self._h)
+                    self._h = None
+                else:
+                    # destroying a multi-rank plan is collective (peers may still write into this rank's buffers): it cannot
+                    # be done from a finaliser.  Say so instead of leaking three exchange buffers silently.
+                    import warnings
+                    warnings.warn("accfft_b200.Plan of a %d-rank communicator was garbage collected without destroy(): its "
+                                  "exchange buffers and IPC mappings are leaked" % self.comm.nprocs, ResourceWarning)
         except Exception:
             pass
 

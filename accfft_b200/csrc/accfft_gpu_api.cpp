@@ -432,7 +432,7 @@ void accfft_divergence_gpu(double* divA, double* A_x, double* A_y, double* A_z, 
   accfft_divergence_gpu_t(divA, A_x, A_y, A_z, plan, timer);
 }
 void accfft_divergence_slow_gpu(double* divA, double* A_x, double* A_y, double* A_z, accfft_plan_gpu* plan, double* timer) {
-  accfft_divergence_gpu_t(divA, A_x, A_y, A_z, plan, timer);
+  accfft_divergence_gpu_slow_t(divA, A_x, A_y, A_z, plan, timer);   // the full 3-D scheme (src/operators_gpu.txx:336-446)
 }
 void accfft_biharmonic_gpu(double* LA, double* A, accfft_plan_gpu* plan, double* timer) {
   accfft_biharmonic_gpu_t(LA, A, plan, timer);
@@ -446,7 +446,7 @@ void accfft_divergence_gpuf(float* divA, float* A_x, float* A_y, float* A_z, acc
   accfft_divergence_gpu_t(divA, A_x, A_y, A_z, plan, timer);
 }
 void accfft_divergence_slow_gpuf(float* divA, float* A_x, float* A_y, float* A_z, accfft_plan_gpuf* plan, double* timer) {
-  accfft_divergence_gpu_t(divA, A_x, A_y, A_z, plan, timer);
+  accfft_divergence_gpu_slow_t(divA, A_x, A_y, A_z, plan, timer);
 }
 void accfft_biharmonic_gpuf(float* LA, float* A, accfft_plan_gpuf* plan, double* timer) {
   accfft_biharmonic_gpu_t(LA, A, plan, timer);

@@ -40,6 +40,8 @@ int accfft_launch_k7_p0(const Launch&, cudaStream_t);
 int accfft_launch_k7_p1(const Launch&, cudaStream_t);
 int accfft_launch_k8_p0(const Launch&, cudaStream_t);   // contiguous (Z-axis) derivative
 int accfft_launch_k8_p1(const Launch&, cudaStream_t);
+int accfft_launch_k9_p0(const Launch&, cudaStream_t);   // strided c2c, wide CTA shape; -2 = the length has none
+int accfft_launch_k9_p1(const Launch&, cudaStream_t);
 int accfft_launch_generic(const Launch&, int realN, cudaStream_t);   // generic_dft.cu: O(N^2) fallback, -1 = not served
 int accfft_generic_max_length(Prec prec);
 int accfft_has_wide_p0(int n);   // does the strided kernel have a wide CTA shape for this length? (k_tu.cu, kind 0)
@@ -271,6 +273,8 @@ struct CudaBackend : Backend {
   int link(int from, int to) override;
   int copy2d(int lane, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) override;
   int local_variant(const Launch& l) override;
+  int l2_planes(const Plan& p) override;
+  int l2_window(const void* ptr, size_t bytes) override;
 };
 
 constexpr size_t kFlagBytes = 4096;
@@ -289,6 +293,9 @@ struct Engine {
   static constexpr int kMaxCopyLanes = 8;
   int ce_chunks = 0;           // ACCFFT_B200_CE: chunks per exchanging stage (0: direct peer stores instead)
   int ce_lanes = 0;            // ACCFFT_B200_CE_LANES: copy streams (copies to different peers overlap)
+  bool l2_persist = false;     // ACCFFT_B200_L2_PERSIST=1: give the hand-off buffer an L2-persisting access-policy window
+  size_t l2_window_max = 0;
+  long long l2_budget = 0;     // ACCFFT_B200_L2_MB: bytes of intermediate planes kept L2-resident between two local passes (0: off)
   int push_ctas = 0;           // ACCFFT_B200_PUSH: CTAs of the TMA push kernel per transfer (0: copy engines / cudaMemcpyAsync)
   cudaStream_t copy_streams[kMaxCopyLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* stage_buf = nullptr;   // local staging buffer of the exchanging stage (one exchange buffer long)
@@ -300,8 +307,9 @@ struct Engine {
   size_t sync_next = 0;
   int tma_mode = 1;            // ACCFFT_B200_TMA: 0 = plain kernel only, 1 = tuned / heuristic, 2 = TMA kernel always, 3 = wide shape always
   bool wired = false;          // peers attached (always true for single-rank plans)
-  char* slab = nullptr;        // [A | B | flags] of this rank
+  char* slab = nullptr;        // [A | B | (A' | B' with double buffering) | flags] of this rank
   size_t slab_bytes = 0, bufsz = 0;
+  int nbuf = 2;                // 4 = double buffered exchange buffers (multi-rank plans; ACCFFT_B200_DB=0: 2)
   void* spec = nullptr;        // lazily allocated spectrum scratch for grad / divergence
   int* status_d = nullptr;     // barrier timeout word
   std::vector<void*> opened;   // cudaIpcOpenMemHandle mappings to close
@@ -427,6 +435,31 @@ int CudaBackend::fork() { return link_streams(e->stream, e->aux); }
 int CudaBackend::hand(int from) { return from == 0 ? link_streams(e->stream, e->aux) : link_streams(e->aux, e->stream); }
 int CudaBackend::join() { return link_streams(e->aux, e->stream); }
 
+// planes per chunk of the L2-resident Z <-> Y hand-off: as many whole i0 planes of the intermediate layout as fit the budget
+int CudaBackend::l2_planes(const Plan& p) {
+  if (e->timing || e->l2_budget <= 0) return 0;
+  const long long cs = p.prec == PREC_DOUBLE ? 16 : 8;
+  const long long plane = (long long)p.g.n[1] * p.g.k2.size * cs;   // bytes of one i0 plane of A ([N1][k2]); B's [i1][n2c] is the same size
+  if (plane <= 0) return 0;
+  const long long planes = e->l2_budget / plane;
+  if (planes < 1 || planes >= p.g.i0.size) return 0;                 // a plane does not fit / the whole array fits: nothing to chunk
+  return (int)planes;
+}
+
+// L2 access-policy window of the plan's stream: hits in the window persist, everything else streams through
+int CudaBackend::l2_window(const void* ptr, size_t bytes) {
+  if (!e->l2_persist) return 0;
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  v.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+  v.accessPolicyWindow.num_bytes = std::min(bytes, e->l2_window_max);
+  v.accessPolicyWindow.hitRatio = 1.0f;
+  v.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+  v.accessPolicyWindow.missProp = bytes ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+  CU(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &v));
+  return 0;
+}
+
 // ---- copy-engine exchange ---------------------------------------------------------------------------------------
 int CudaBackend::ce_chunks() { return (e->timing || !e->stage_buf || e->ce_lanes < 1) ? 0 : e->ce_chunks; }
 int CudaBackend::copy_lanes() { return e->ce_lanes; }
@@ -543,13 +576,10 @@ int CudaBackend::launch(const Launch& l) {
       rc = -2;
       if (v == 2 || l.dry) rc = sel == 0 ? accfft_launch_k4_p0(l, e->stream) : accfft_launch_k4_p1(l, e->stream);
       if (rc == -2 || (l.dry && rc == 0)) {
-        Launch lv = l;
-        lv.variant = v == 3 ? 3 : 1;
-        rc = sel == 0 ? accfft_launch_k0_p0(lv, e->stream) : accfft_launch_k0_p1(lv, e->stream);
-        if (rc == -2) {   // wide shape not available for this length
-          lv.variant = 1;
-          rc = sel == 0 ? accfft_launch_k0_p0(lv, e->stream) : accfft_launch_k0_p1(lv, e->stream);
-        }
+        rc = -2;
+        if (v == 3 || l.dry) rc = sel == 0 ? accfft_launch_k9_p0(l, e->stream) : accfft_launch_k9_p1(l, e->stream);
+        if (rc == -2 || (l.dry && rc == 0))   // default shape (also when the length has no wide shape)
+          rc = sel == 0 ? accfft_launch_k0_p0(l, e->stream) : accfft_launch_k0_p1(l, e->stream);
       }
       break;
     }
@@ -641,7 +671,13 @@ static void wire_self(Engine* e) {
   e->flag_ptrs.assign(np, nullptr);
   e->plan.peerA[e->rank] = e->slab;
   e->plan.peerB[e->rank] = e->slab + e->bufsz;
-  e->flag_ptrs[e->rank] = (unsigned long long*)(e->slab + 2 * e->bufsz);
+  if (e->nbuf == 4) {
+    e->plan.peerA_alt.assign(np, nullptr);
+    e->plan.peerB_alt.assign(np, nullptr);
+    e->plan.peerA_alt[e->rank] = e->slab + 2 * e->bufsz;
+    e->plan.peerB_alt[e->rank] = e->slab + 3 * e->bufsz;
+  }
+  e->flag_ptrs[e->rank] = (unsigned long long*)(e->slab + (size_t)e->nbuf * e->bufsz);
 }
 
 // size of rank q's exchange buffers (256-byte aligned) -- every rank can compute it for every peer
@@ -846,10 +882,13 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
   cudaError_t err = cudaGetDevice(&e->device);
   if (err == cudaSuccess) {
     e->bufsz = bufsz_of(e, rank);
-    e->slab_bytes = 2 * e->bufsz + kFlagBytes;
+    e->nbuf = pl.nprocs > 1 ? 4 : 2;
+    if (const char* m = getenv("ACCFFT_B200_DB"))
+      if (m[0] == '0') e->nbuf = 2;
+    e->slab_bytes = (size_t)e->nbuf * e->bufsz + kFlagBytes;
     err = cudaMalloc((void**)&e->slab, e->slab_bytes);
   }
-  if (err == cudaSuccess) err = cudaMemset(e->slab + 2 * e->bufsz, 0, kFlagBytes);
+  if (err == cudaSuccess) err = cudaMemset(e->slab + (size_t)e->nbuf * e->bufsz, 0, kFlagBytes);
   // spectrum scratch of the operators: allocated now, never inside a collective call (cudaMalloc synchronises
   // the device, which must not happen while a peer's barrier kernel waits for this rank)
   if (err == cudaSuccess && kind == ACCFFTB_R2C) err = cudaMalloc(&e->spec, e->bufsz);
@@ -915,6 +954,18 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
         }
       }
     }
+    if (const char* m = getenv("ACCFFT_B200_L2_MB")) e->l2_budget = (long long)atoi(m) << 20;
+    if (const char* m = getenv("ACCFFT_B200_L2_PERSIST")) e->l2_persist = atoi(m) != 0;
+    if (e->l2_budget > 0 && e->l2_persist) {
+      int max_persist = 0, max_window = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+      e->l2_window_max = (size_t)max_window;
+      if (max_persist <= 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)e->l2_budget, (size_t)max_persist)) != cudaSuccess) {
+        cudaGetLastError();
+        e->l2_persist = false;
+      }
+    }
     if (const char* m = getenv("ACCFFT_B200_TMA")) e->tma_mode = m[0] == '0' ? 0 : m[0] == '2' ? 2 : m[0] == '3' ? 3 : 1;
     // ACCFFT_MEASURE / ACCFFT_PATIENT: pick the faster kernel per strided stage by timing both (plan-owned buffers only)
     if (!rc && (flags & (ACCFFTB_MEASURE | ACCFFTB_PATIENT)) && e->tma_mode == 1) rc = autotune(e);
@@ -953,15 +1004,19 @@ int accfftb_plan_ipc_import(accfftb_plan* plan, const void* blobs, int nblobs) {
     if (b.magic != 0xACCFF7B2u || b.rank != q || b.nprocs != nblobs)
       return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: blob " + std::to_string(q) + " is not rank-ordered / valid");
     const size_t bs = bufsz_of(e, q);
-    if (b.slab_bytes != 2 * bs + kFlagBytes)
-      return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: peer plan geometry differs");
+    if (b.slab_bytes != (size_t)e->nbuf * bs + kFlagBytes)
+      return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: peer plan geometry (or its buffering mode) differs");
     if (q == e->rank) continue;
     void* base = nullptr;
     CU(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
     e->opened.push_back(base);
     e->plan.peerA[q] = base;
     e->plan.peerB[q] = (char*)base + bs;
-    e->flag_ptrs[q] = (unsigned long long*)((char*)base + 2 * bs);
+    if (e->nbuf == 4) {
+      e->plan.peerA_alt[q] = (char*)base + 2 * bs;
+      e->plan.peerB_alt[q] = (char*)base + 3 * bs;
+    }
+    e->flag_ptrs[q] = (unsigned long long*)((char*)base + (size_t)e->nbuf * bs);
   }
   e->wired = true;
   return 0;
@@ -981,9 +1036,14 @@ int accfftb_plan_attach_local_peers(accfftb_plan* plan, accfftb_plan* const* pla
       if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
       else if (err != cudaSuccess) return cuda_fail(err, "cudaDeviceEnablePeerAccess");
     }
+    if (o->nbuf != e->nbuf) return fail(ACCFFTB_ERR_ARG, "plans differ in their buffering mode");
     e->plan.peerA[q] = o->slab;
     e->plan.peerB[q] = o->slab + o->bufsz;
-    e->flag_ptrs[q] = (unsigned long long*)(o->slab + 2 * o->bufsz);
+    if (e->nbuf == 4) {
+      e->plan.peerA_alt[q] = o->slab + 2 * o->bufsz;
+      e->plan.peerB_alt[q] = o->slab + 3 * o->bufsz;
+    }
+    e->flag_ptrs[q] = (unsigned long long*)(o->slab + (size_t)o->nbuf * o->bufsz);
   }
   e->wired = true;
   return 0;
@@ -1178,12 +1238,16 @@ static int div_impl(accfftb_plan* plan, const void* Ax, const void* Ay, const vo
   const int xyz = 7;
   CHECK_PLAN(plan, true);
   if (!Ax || !Ay || !Az || !div) return fail(ACCFFTB_ERR_ARG, "null data pointer");
-  if (!slow && (div == Ax || div == Ay || div == Az)) return fail(ACCFFTB_ERR_ARG, "divergence output must not alias an input component");
   Engine* e = &plan->e;
   int rc = ensure_spec(e);
   if (rc) return rc;
   TimerScope ts(e, timer, 7);
   const void* ins[3] = {Ax, Ay, Az};
+  // The per-axis scheme accumulates into the output while it still reads inputs: an output that aliases a component (the
+  // reference's fast divergence tolerates divA == A_x, src/operators_gpu.txx:448-553) goes through the 3-D scheme instead,
+  // with the per-axis scheme's Nyquist rule -- the same operator; its output is written only after all inputs are consumed.
+  const bool aliased = div == Ax || div == Ay || div == Az;
+  if (!slow && aliased) return engine_finish(e, e->plan.execute_divergence(ins, div, e->spec, true));
   return engine_finish(e, slow ? e->plan.execute_divergence(ins, div, e->spec) : e->plan.execute_divergence_axes(ins, div, e->spec));
 }
 

@@ -25,7 +25,7 @@
 // out-of-line device functions (the spectral-operator multiply): ONE copy per translation unit instead of one inlined
 // copy per transform element and kernel -- the stage kernels shrank ~5x when apply_op left their bodies
 #if defined(__CUDACC__)
-#define ACC_HD_NOINLINE __host__ __device__ __noinline__
+#define ACC_HD_NOINLINE static __host__ __device__ __noinline__   // (static: one private copy per translation unit)
 #else
 #define ACC_HD_NOINLINE inline
 #endif
@@ -43,9 +43,36 @@ struct alignas(2 * sizeof(T)) cplx {
   T x, y;
 };
 
+// Two single-precision lanes handled as ONE scalar: cplx<f2> = {re0, re1, im0, im1} is a pair of complex floats (two
+// adjacent columns of a strided stage), 16 bytes like a complex double.  Every butterfly below is written with + - * on its
+// scalar type only, so the whole engine runs on cplx<f2> unchanged: the single-precision strided kernels move 128-bit
+// quantities through registers and shared memory exactly like the double-precision ones (stage.cuh: strided_c2c_pair_body).
+struct f2 {
+  float a, b;
+  f2() = default;
+  ACC_HD f2(float s) : a(s), b(s) {}
+  ACC_HD f2(double s) : a((float)s), b((float)s) {}
+  ACC_HD f2(int s) : a((float)s), b((float)s) {}
+  ACC_HD f2(float a_, float b_) : a(a_), b(b_) {}
+};
+ACC_HD f2 operator+(f2 u, f2 v) { return {u.a + v.a, u.b + v.b}; }
+ACC_HD f2 operator-(f2 u, f2 v) { return {u.a - v.a, u.b - v.b}; }
+ACC_HD f2 operator*(f2 u, f2 v) { return {u.a * v.a, u.b * v.b}; }
+ACC_HD f2 operator*(f2 u, float s) { return {u.a * s, u.b * s}; }
+ACC_HD f2 operator*(float s, f2 u) { return {u.a * s, u.b * s}; }
+ACC_HD f2 operator-(f2 u) { return {-u.a, -u.b}; }
+
+// scalar type of the twiddle factors that go with a value type
+template <class T> struct twiddle_of { using type = T; };
+template <> struct twiddle_of<f2> { using type = float; };
+
 template <class T> ACC_HD cplx<T> cadd(cplx<T> a, cplx<T> b) { return {a.x + b.x, a.y + b.y}; }
 template <class T> ACC_HD cplx<T> csub(cplx<T> a, cplx<T> b) { return {a.x - b.x, a.y - b.y}; }
 template <class T> ACC_HD cplx<T> cmul(cplx<T> a, cplx<T> b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+// value times twiddle (the twiddle may be a plain float while the value is a lane pair)
+template <class T, class TW> ACC_HD cplx<T> cmul_tw(cplx<T> a, cplx<TW> b) {
   return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }
 template <class T> ACC_HD cplx<T> cconj(cplx<T> a) { return {a.x, -a.y}; }
@@ -392,28 +419,28 @@ ACC_HD void load_base_twiddles(cplx<T>* w1, int t, const cplx<T>* __restrict__ t
   load_base_twiddles_pass<S, 3, TWS>(w1, t, tw);
 }
 
-template <int R, class T>
-ACC_HD void apply_twiddle_powers(cplx<T>* v, cplx<T> w1) {
-  cplx<T> w[R > 2 ? R : 2];
+template <int R, class T, class TW>
+ACC_HD void apply_twiddle_powers(cplx<T>* v, cplx<TW> w1) {
+  cplx<TW> w[R > 2 ? R : 2];
   w[1] = w1;
-  v[1] = cmul(v[1], w1);
+  v[1] = cmul_tw(v[1], w1);
   ACC_UNROLL
   for (int r = 2; r < R; ++r) {
     const int h = r >> 1;
-    if (r == 2 * h) w[r] = {w[h].x * w[h].x - w[h].y * w[h].y, T(2) * w[h].x * w[h].y};
+    if (r == 2 * h) w[r] = {w[h].x * w[h].x - w[h].y * w[h].y, TW(2) * w[h].x * w[h].y};
     else w[r] = cmul(w[h], w[r - h]);
-    v[r] = cmul(v[r], w[r]);
+    v[r] = cmul_tw(v[r], w[r]);
   }
 }
 
-template <class S, int P, class T>
-ACC_HD void pass_compute(cplx<T>* v, int t, const cplx<T>* w1) {
+template <class S, int P, class T, class TW>
+ACC_HD void pass_compute(cplx<T>* v, int t, const cplx<TW>* w1) {
   constexpr int R = S::radix(P), NS = S::ns(P), NB = S::nb(P), CNT = S::cnt(P);
   ACC_UNROLL
   for (int u = 0; u < CNT; ++u) {
     const int j = t + u * S::G;
     if (CNT * S::G == NB || j < NB) {
-      if constexpr (NS > 1) apply_twiddle_powers<R, T>(v + u * R, w1[S::tw_off(P) + u]);
+      if constexpr (NS > 1) apply_twiddle_powers<R, T, TW>(v + u * R, w1[S::tw_off(P) + u]);
       Dft<R, 1, T>::run(v + u * R);
     }
   }
@@ -466,8 +493,8 @@ ACC_HD void pass_foreach(cplx<T>* v, int t, F f) {
 // registers hold the final outputs in pass-(NP-1) gather order (index j + r*N/R_last).
 // w1: base twiddles from load_base_twiddles.  smem_addr(i) -> pointer to this column's slot i;
 // sync() is a CTA-wide barrier.
-template <class S, class T, class Addr, class Sync>
-ACC_HD void fft_passes(cplx<T>* v, int t, const cplx<T>* w1, Addr smem_addr, Sync sync) {
+template <class S, class T, class TW, class Addr, class Sync>
+ACC_HD void fft_passes(cplx<T>* v, int t, const cplx<TW>* w1, Addr smem_addr, Sync sync) {
   pass_compute<S, 0>(v, t, w1);
   if constexpr (S::NP > 1) {
     pass_scatter<S, 0>(v, t, smem_addr);

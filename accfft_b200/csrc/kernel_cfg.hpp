@@ -37,6 +37,22 @@ struct CfgW {
   static constexpr int STRIDED_SMEM = S::SMEM_ELEMS * TC * (int)sizeof(cplx<T>);
 };
 
+// single-precision pair kernel (stage.cuh: strided_c2c_pair_body): TCP pair-columns (= 2 * TCP columns) per tile
+template <class S>
+struct PairCfg {
+  static constexpr int pick() {
+    int tc = 8;   // 16 columns = 128-byte rows
+    while (tc > 1 && (S::G * tc > ACCFFT_MAX_STRIDED_THREADS || (long long)S::SMEM_ELEMS * tc * 16 > ACCFFT_MAX_STRIDED_SMEM)) tc /= 2;
+    return tc;
+  }
+  static constexpr int TCP = pick();
+  static constexpr int THREADS = S::G * TCP;
+  static constexpr int SMEM = S::SMEM_ELEMS * TCP * 16;
+  // resident CTAs the kernel is compiled for: 1024 threads per SM (<= 64 registers) when a thread holds up to 8 lane pairs;
+  // schedules with 16 values per thread (e.g. the single-precision 1024-point one) get the full register file instead
+  static constexpr int MINB = S::NREG > 8 ? 1 : ((1024 / THREADS) > 0 ? (1024 / THREADS) : 1);
+};
+
 template <class T, class S>
 struct Cfg {
   static constexpr int TC = strided_tc_pick<T, S>(ACCFFT_MAX_STRIDED_THREADS, ACCFFT_MAX_STRIDED_SMEM);

@@ -46,6 +46,13 @@ __global__ void __launch_bounds__(Cfg<T, S>::STRIDED_THREADS, (1024 / Cfg<T, S>:
   CudaCtx ctx;
   strided_c2c_body<T, S, Cfg<T, S>::TC, GEN>(d, ctx);
 }
+// single precision: two adjacent columns per thread as one 16-byte quantity (stage.cuh: strided_c2c_pair_body)
+template <class S, bool GEN>
+__global__ void __launch_bounds__(PairCfg<S>::THREADS, PairCfg<S>::MINB)
+    k_strided_c2c_pair(const __grid_constant__ StageDesc d) {
+  CudaCtx ctx;
+  strided_c2c_pair_body<S, PairCfg<S>::TCP, GEN>(d, ctx);
+}
 // same body, wide CTA shape (kernel_cfg.hpp: CfgW); instantiated only where it differs from the default shape
 template <class T, class S, bool GEN>
 __global__ void __launch_bounds__(CfgW<T, S>::STRIDED_THREADS, 1) k_strided_c2c_wide(const __grid_constant__ StageDesc d) {
@@ -162,21 +169,30 @@ static int launch_one(const Launch& l, cudaStream_t st) {
 #endif
   const bool gen = !stage_is_simple(d);
   (void)gen;
-#if ACCFFT_KIND == 0
+#if ACCFFT_KIND == 9
+  // wide CTA shape of the plain strided kernel (its own translation unit: k9)
   if constexpr (C::HAS_WIDE) {
     using W = CfgW<T, S>;
-    if (l.dry || l.variant == 3) {
-      const long long nbw = (long long)d.nA * ((d.nB + d.colShift + W::TC - 1) / W::TC);
-      const int rc = launch_pair(k_strided_c2c_wide<T, S, false>, k_strided_c2c_wide<T, S, true>, gen, nbw, W::STRIDED_THREADS,
-                                 W::STRIDED_SMEM, W::STRIDED_SMEM, d, st, l.dry);
-      if (!l.dry || rc) return rc;
-    }
-  } else if (l.variant == 3 && !l.dry) {
-    return -2;   // no wide shape for this length / precision: the caller falls back to the default shape
+    const long long nbw = (long long)d.nA * ((d.nB + d.colShift + W::TC - 1) / W::TC);
+    return launch_pair(k_strided_c2c_wide<T, S, false>, k_strided_c2c_wide<T, S, true>, gen, nbw, W::STRIDED_THREADS,
+                       W::STRIDED_SMEM, W::STRIDED_SMEM, d, st, l.dry);
+  } else {
+    return l.dry ? 0 : -2;   // no wide shape for this length / precision: the caller falls back to the default shape
   }
-  const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
-  return launch_pair(k_strided_c2c<T, S, false>, k_strided_c2c<T, S, true>, gen, nb, C::STRIDED_THREADS, C::STRIDED_SMEM,
-                     C::STRIDED_SMEM, d, st, l.dry);
+#elif ACCFFT_KIND == 0
+  if constexpr (sizeof(T) == 4) {
+    // single precision: the default shape is the pair kernel (every strided stage has unit column stride on its input side;
+    // the 8-byte-element form of the plain kernel is not instantiated at all)
+    using PC = PairCfg<S>;
+    if (d.inStrideB != 1 && !l.dry) return (int)cudaErrorInvalidValue;
+    const long long nbp = (long long)d.nA * ((d.nB + d.colShift + 2 * PC::TCP - 1) / (2 * PC::TCP));
+    return launch_pair(k_strided_c2c_pair<S, false>, k_strided_c2c_pair<S, true>, gen, nbp, PC::THREADS, PC::SMEM, PC::SMEM, d, st,
+                       l.dry);
+  } else {
+    const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
+    return launch_pair(k_strided_c2c<T, S, false>, k_strided_c2c<T, S, true>, gen, nb, C::STRIDED_THREADS, C::STRIDED_SMEM,
+                       C::STRIDED_SMEM, d, st, l.dry);
+  }
 #elif ACCFFT_KIND == 8
   const long long npairs = ((long long)d.nA * d.nB + 1) / 2;
   return launch_kernel(k_contig_deriv<T, S>, (npairs + C::PC - 1) / C::PC, C::CONTIG_THREADS, C::CONTIG_SMEM, d, st, l.dry);
@@ -206,7 +222,7 @@ static int launch_one(const Launch& l, cudaStream_t st) {
 }
 
 #endif
-#if ACCFFT_KIND == 0
+#if ACCFFT_KIND == 9
 // does this length / precision have a wide CTA shape (kernel_cfg.hpp: CfgW)?  Host-side query for the variant choice.
 template <class T>
 static int has_wide_any(int n) {

@@ -434,7 +434,67 @@ static Launch restrict_b(Launch l, int b0, int nb, size_t in_elem, size_t out_el
   return l;
 }
 
+// ================================================================================================================
+// L2-resident hand-off between the two LOCAL passes of a transform (single rank; slab grids for the pair that stays local).
+// Forward: Z then Y both walk the outer index i0, and Y(i0) needs nothing but Z(i0)'s plane.  Run them chunk by chunk over
+// i0 with the intermediate planes in ONE small buffer (the head of A) that every chunk reuses: at `planes` x plane bytes
+// well under the 126 MB L2 the Z stage's stores are still resident when the Y stage reads them, and because the next chunk
+// overwrites the same lines they are never written back either -- the intermediate array's HBM write AND read disappear
+// (2 of the 6 array passes' worth of traffic per transform: R + 5C -> R + 3C).  Inverse: Y then Z, same thing through the
+// head of B.  The reference's analogue is the hand-off between cufftExecD2Z and the per-slab Y loop
+// (src/accfft_gpu.cpp:477-516), which goes through global memory for the whole array.
+// ================================================================================================================
+static Launch chunk_a(Launch l, int a0, int na, size_t in_elem, size_t out_elem, bool move_in, bool move_out) {
+  StageDesc& d = l.desc;
+  if (move_in) d.in = (const char*)d.in + (long long)a0 * d.inStrideA * (long long)in_elem;
+  if (move_out)
+    for (int s = 0; s < d.nseg; ++s) d.seg[s].base = (char*)d.seg[s].base + (long long)a0 * d.seg[s].strideA * (long long)out_elem;
+  d.nA = na;
+  return l;
+}
+
+int Plan::forward_zy_l2(const void* in, bool in_padded, int planes) {
+  int rc;
+  const size_t cs = prec == PREC_DOUBLE ? 16 : 8;
+  const size_t in_elem = g.r2c ? cs / 2 : cs;
+  const Launch z = fwd_z(in, in_padded), y = fwd_y();
+  const int n = g.i0.size;
+  if ((rc = be->l2_window(y.desc.in, (size_t)planes * (size_t)y.desc.inStrideA * cs))) return rc;
+  for (int a0 = 0; a0 < n; a0 += planes) {
+    const int na = std::min(planes, n - a0);
+    Launch zc = chunk_a(z, a0, na, in_elem, cs, true, false);    // input advances, output = head of A
+    if (!empty(zc) && (rc = be->launch(zc))) return rc;
+    Launch yc = chunk_a(y, a0, na, cs, cs, false, true);         // input = head of A, output advances
+    if (!empty(yc) && (rc = be->launch(yc))) return rc;
+  }
+  return be->l2_window(nullptr, 0);
+}
+
+int Plan::inverse_yz_l2(void* out, bool out_padded, int planes) {
+  int rc;
+  const size_t cs = prec == PREC_DOUBLE ? 16 : 8;
+  const size_t out_elem = g.r2c ? cs / 2 : cs;
+  const Launch y = inv_y(), z = inv_z(out, out_padded);
+  const int n = g.i0.size;
+  if ((rc = be->l2_window(z.desc.in, (size_t)planes * (size_t)z.desc.inStrideA * cs))) return rc;
+  for (int a0 = 0; a0 < n; a0 += planes) {
+    const int na = std::min(planes, n - a0);
+    Launch yc = chunk_a(y, a0, na, cs, cs, true, false);         // input advances through A, output = head of B
+    if (!empty(yc) && (rc = be->launch(yc))) return rc;
+    Launch zc = chunk_a(z, a0, na, cs, out_elem, false, true);   // input = head of B, output advances
+    if (!empty(zc) && (rc = be->launch(zc))) return rc;
+  }
+  return be->l2_window(nullptr, 0);
+}
+
+int Plan::bar_if(bool data) {
+  if (nprocs <= 1) return 0;
+  if (db() && !data) return 0;
+  return bar();
+}
+
 int Plan::a_fence() {
+  if (db()) return 0;   // double buffering: the peers' late reads concern the other buffer set
   if (!late_a_reader) return 0;
   return nprocs > 1 ? bar() : 0;
 }
@@ -596,7 +656,14 @@ int Plan::inverse_slab_ce(const void* in, void* out, bool out_padded) {
 
 int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
   int rc;
+  flip();
   if (use_ce(xyz)) return forward_slab_ce(in, out, in_padded);
+  if (xyz == 7 && nprocs == 1 && be->l2_planes(*this) > 0) {
+    if ((rc = forward_zy_l2(in, in_padded, be->l2_planes(*this)))) return rc;
+    Launch x = fwd_x(out);
+    if (!empty(x) && (rc = be->launch(x))) return rc;
+    return 0;
+  }
   if (xyz == 7 && nprocs > 1 && g.np[1] == 1 && be->pipeline_chunks() > 1) {
     if ((rc = forward_zy_pipelined(in, in_padded, be->pipeline_chunks()))) return rc;
     if ((rc = bar())) return rc;
@@ -607,11 +674,11 @@ int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
   Launch z = fwd_z(in, in_padded);
   if (!(xyz & 4)) no_transform(z, g.n[2]);
   if (!empty(z) && (rc = be->launch(z))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch y = fwd_y();
   if (!(xyz & 2)) no_transform(y, g.n[1]);
   if (!empty(y) && (rc = be->launch(y))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(col_exchanges()))) return rc;
   Launch x = fwd_x(out);
   if (!(xyz & 1)) no_transform(x, g.n[0]);
   if (!empty(x) && (rc = be->launch(x))) return rc;
@@ -620,16 +687,22 @@ int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
 
 int Plan::execute_inverse(const void* in, void* out, bool out_padded, int xyz) {
   int rc;
+  flip();
   if (use_ce(xyz)) return inverse_slab_ce(in, out, out_padded);
+  if (xyz == 7 && nprocs == 1 && be->l2_planes(*this) > 0) {
+    Launch x = inv_x(in);
+    if (!empty(x) && (rc = be->launch(x))) return rc;
+    return inverse_yz_l2(out, out_padded, be->l2_planes(*this));
+  }
   if ((rc = a_fence())) return rc;
   Launch x = inv_x(in);
   if (!(xyz & 1)) no_transform(x, g.n[0]);
   if (!empty(x) && (rc = be->launch(x))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(col_exchanges()))) return rc;
   Launch y = inv_y();
   if (!(xyz & 2)) no_transform(y, g.n[1]);
   if (!empty(y) && (rc = be->launch(y))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch z = inv_z(out, out_padded);
   if (!(xyz & 4)) no_transform(z, g.n[2]);
   if (!empty(z) && (rc = be->launch(z))) return rc;
@@ -638,12 +711,13 @@ int Plan::execute_inverse(const void* in, void* out, bool out_padded, int xyz) {
 
 int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double opA, double opB) {
   int rc;
+  flip();
   Launch z = fwd_z(in, false);
   if (!empty(z) && (rc = be->launch(z))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch y = fwd_y();
   if (!empty(y) && (rc = be->launch(y))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(col_exchanges()))) return rc;
   // X forward with the symbol multiply and the 1/N normalisation fused into its stores, into `spec`
   // (user spectrum layout), which the inverse X stage reads back
   Launch x = fwd_x(spec);
@@ -652,12 +726,13 @@ int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double
   x.desc.opB = opB;
   x.desc.scale = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
   if (!empty(x) && (rc = be->launch(x))) return rc;
+  flip();
   Launch xi = inv_x(spec);
   if (!empty(xi) && (rc = be->launch(xi))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(col_exchanges()))) return rc;
   Launch yi = inv_y();
   if (!empty(yi) && (rc = be->launch(yi))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch zi = inv_z(out, false);
   if (!empty(zi) && (rc = be->launch(zi))) return rc;
   return 0;
@@ -666,18 +741,20 @@ int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double
 int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spec, bool pair_rule) {
   int rc;
   const double inv_n = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
+  flip();
   Launch z = fwd_z(in, false);
   if (!empty(z) && (rc = be->launch(z))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch y = fwd_y();
   if (!empty(y) && (rc = be->launch(y))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(col_exchanges()))) return rc;
   Launch x = fwd_x(spec);
   x.desc.op = OP_SCALE;
   x.desc.scale = inv_n;
   if (!empty(x) && (rc = be->launch(x))) return rc;
   for (int ax = 0; ax < 3; ++ax) {
     if (!(comps & (1 << ax))) continue;
+    flip();
     Launch xi = inv_x(spec);
     xi.desc.op = OP_GRAD;
     xi.desc.opAxis = ax;
@@ -685,10 +762,10 @@ int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spe
     xi.desc.opOnLoad = 1;
     xi.desc.opFullAxis = pair_rule ? 0 : 1;
     if (!empty(xi) && (rc = be->launch(xi))) return rc;
-    if (nprocs > 1 && (rc = bar())) return rc;
+    if ((rc = bar_if(col_exchanges()))) return rc;
     Launch yi = inv_y();
     if (!empty(yi) && (rc = be->launch(yi))) return rc;
-    if (nprocs > 1 && (rc = bar())) return rc;
+    if ((rc = bar_if(row_exchanges()))) return rc;
     Launch zi = inv_z(outs[ax], false);
     if (!empty(zi) && (rc = be->launch(zi))) return rc;
   }
@@ -699,12 +776,13 @@ int Plan::execute_divergence(const void* const ins[3], void* out, void* spec, bo
   int rc;
   const double inv_n = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
   for (int ax = 0; ax < 3; ++ax) {
+    flip();
     Launch z = fwd_z(ins[ax], false);
     if (!empty(z) && (rc = be->launch(z))) return rc;
-    if (nprocs > 1 && (rc = bar())) return rc;
+    if ((rc = bar_if(row_exchanges()))) return rc;
     Launch y = fwd_y();
     if (!empty(y) && (rc = be->launch(y))) return rc;
-    if (nprocs > 1 && (rc = bar())) return rc;
+    if ((rc = bar_if(col_exchanges()))) return rc;
     Launch x = fwd_x(spec);
     x.desc.op = OP_GRAD;
     x.desc.opAxis = ax;
@@ -713,12 +791,13 @@ int Plan::execute_divergence(const void* const ins[3], void* out, void* spec, bo
     x.desc.accumulate = ax > 0;
     if (!empty(x) && (rc = be->launch(x))) return rc;
   }
+  flip();
   Launch xi = inv_x(spec);
   if (!empty(xi) && (rc = be->launch(xi))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(col_exchanges()))) return rc;
   Launch yi = inv_y();
   if (!empty(yi) && (rc = be->launch(yi))) return rc;
-  if (nprocs > 1 && (rc = bar())) return rc;
+  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch zi = inv_z(out, false);
   if (!empty(zi) && (rc = be->launch(zi))) return rc;
   return 0;
@@ -906,6 +985,7 @@ int Plan::execute_r2c_axis(int axis, const void* in, void* out) {
   }
   const bool ex = ax_exchanges(axis);
   if (ex) {
+    flip();
     if ((rc = a_fence())) return rc;
     Launch c = ax_copy_in(axis, in);
     if (!empty(c) && (rc = be->launch(c))) return rc;
@@ -913,7 +993,7 @@ int Plan::execute_r2c_axis(int axis, const void* in, void* out) {
   }
   Launch s = ax_stage(axis, AX_R2C, in, out);
   if (!empty(s) && (rc = be->launch(s))) return rc;
-  if (ex && (rc = bar())) return rc;   // A was read after the exchange barrier: fence it from the next operation
+  if (ex && (rc = bar_if(false))) return rc;   // A was read after the exchange barrier: fence it from the next operation (reuse only)
   return 0;
 }
 
@@ -928,7 +1008,8 @@ int Plan::execute_c2r_axis(int axis, const void* in, void* out) {
     return empty(z) ? 0 : be->launch(z);
   }
   const bool ex = ax_exchanges(axis);
-  if (ex && (rc = bar())) return rc;   // B is written first thing: wait for the peers' previous operation
+  if (ex) flip();
+  if (ex && (rc = bar_if(false))) return rc;   // B is written first thing: wait for the peers' previous operation (reuse only)
   Launch s = ax_stage(axis, AX_C2R, in, out);
   if (!empty(s) && (rc = be->launch(s))) return rc;
   if (ex) {
@@ -980,6 +1061,7 @@ int Plan::execute_deriv_axis(int axis, const void* in, void* out, bool accumulat
   }
   const bool ex = ax_exchanges(axis);
   if (ex) {
+    flip();
     if ((rc = a_fence())) return rc;
     Launch c = ax_copy_in(axis, in);
     if (!empty(c) && (rc = be->launch(c))) return rc;

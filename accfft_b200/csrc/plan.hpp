@@ -50,6 +50,11 @@ struct Backend {
   virtual int link(int, int) { return 0; }
   virtual int copy2d(int, void*, size_t, const void*, size_t, size_t, size_t) { return -1; }
   virtual int local_variant(const Launch&) { return 0; }
+  // L2-resident hand-off between two local passes (Plan::forward_zy_l2 / inverse_yz_l2): how many i0 planes per chunk;
+  // <= 0: one launch per pass over the whole array
+  virtual int l2_planes(const struct Plan&) { return 0; }
+  // mark [ptr, ptr + bytes) as the L2-persisting window of the stages launched from now on (bytes == 0: no window)
+  virtual int l2_window(const void*, size_t) { return 0; }
 };
 
 struct Geometry {
@@ -79,6 +84,22 @@ struct Plan {
   int nprocs;
   // exchange buffers of every rank of the comm as seen from this rank (self = local pointers)
   std::vector<void*> peerA, peerB;
+  // Double buffering (multi-rank plans): a second set of exchange buffers; every operation that exchanges starts with
+  // flip().  An operation may then write its peers' buffers right away -- the peers last touched this set two exchanging
+  // operations ago, and everybody has passed a barrier of the operation in between -- so barriers are needed only where
+  // they order DATA (a stage reads what peers wrote), not buffer reuse: one barrier per transform on slab grids instead of
+  // two.  Empty alt vectors = single buffering (every barrier stays).
+  std::vector<void*> peerA_alt, peerB_alt;
+  bool db() const { return nprocs > 1 && !peerA_alt.empty(); }
+  void flip() {
+    if (db()) {
+      peerA.swap(peerA_alt);
+      peerB.swap(peerB_alt);
+    }
+  }
+  bool row_exchanges() const { return g.np[1] > 1; }   // Z <-> Y hand-off crosses ranks
+  bool col_exchanges() const { return g.np[0] > 1; }   // Y <-> X hand-off crosses ranks
+  int bar_if(bool data);   // barrier if it orders data, or (single buffering) buffer reuse
   std::string error;
   // Buffer B uses a padded row pitch when there are peers: its rows hold k2.size (forward) or N2c (inverse)
   // complex elements but start every `pad_elems()` elements (128 bytes), so that the 128-byte row segments the
@@ -131,6 +152,8 @@ struct Plan {
   int forward_zy_pipelined(const void* in, bool in_padded, int nch);
   // slab grids: exchange through a local staging buffer + copy-engine transfers, overlapped with the neighbouring stages
   bool use_ce(int xyz) { return xyz == 7 && nprocs > 1 && g.np[1] == 1 && be->ce_chunks() > 0 && be->staging() != nullptr; }
+  int forward_zy_l2(const void* in, bool in_padded, int planes);
+  int inverse_yz_l2(void* out, bool out_padded, int planes);
   int forward_slab_ce(const void* in, void* out, bool in_padded);
   int inverse_slab_ce(const void* in, void* out, bool out_padded);
   // The copy-engine inverse reads A after its last barrier.  Operations that write peers' A right at their start (the

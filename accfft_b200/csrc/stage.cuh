@@ -105,50 +105,91 @@ ACC_HD int freq_index(const StageDesc& d, int ax, int k, int a, int b) {
   }
 }
 
-template <class T>
-ACC_HD_NOINLINE cplx<T> apply_op_impl(const StageDesc& d, cplx<T> v, int k, int a, int b) {
-  if (d.op == OP_SCALE) return {T(v.x * d.scale), T(v.y * d.scale)};
+// The symbol multiply, split in two so that nothing column-invariant is recomputed per element:
+//   op_prepare(d, a, b)        once per thread (out of line): what the two axes that are FIXED for column (a, b) contribute
+//   apply_op(d, col, v, k)     per element: the wave number of the transform axis (index k) + the symbol itself
+// (the transform axis is the one with d.kind[ax] == 0; for OP_GRAD the derivative axis may be the transform axis or a fixed one)
+struct OpCol {
+  double s_other;   // sum of the squared wave numbers of the fixed axes (laplace family)
+  double g_fixed;   // OP_GRAD along a FIXED axis: scale * wave number of that axis for this column
+  int kax;          // the transform axis
+};
+
+ACC_HD long long wave_number_plain(int X, int N) { return X > N / 2 ? (long long)X - N : (long long)X; }
+
+ACC_HD_NOINLINE OpCol op_prepare(const StageDesc& d, int a, int b) {
+  OpCol c;
+  c.s_other = 0.0;
+  c.g_fixed = 0.0;
+  c.kax = d.kind[0] == 0 ? 0 : d.kind[1] == 0 ? 1 : 2;
+  if (d.op == OP_GRAD) {
+    const int ax = d.opAxis;
+    if (d.kind[ax] == 0) {
+      c.kax = ax;
+    } else {
+      const int X = freq_index(d, ax, 0, a, b), N = d.n[ax];
+      c.g_fixed = (X == N - N / 2 && !d.opFullAxis) ? 0.0 : d.scale * (double)wave_number(X, N);
+    }
+    return c;
+  }
+  if (d.op == OP_SCALE || d.op == OP_NONE) return c;
+  for (int ax = 0; ax < 3; ++ax) {
+    if (ax == c.kax) continue;
+    const int X = freq_index(d, ax, 0, a, b);
+    // the reference's inv_biharmonic has the Nyquist rule commented out (src/operators.txx:362-375)
+    const long long w = d.op == OP_INV_BIHARMONIC ? wave_number_plain(X, d.n[ax]) : wave_number(X, d.n[ax]);
+    c.s_other += (double)(w * w);
+  }
+  return c;
+}
+
+// The symbol's (real) weight for transform index k of a prepared column -- out of line: ONE copy of the double-precision
+// symbol arithmetic per translation unit instead of one per unrolled element of every general kernel (the general
+// kernels shrank by a third; the call costs a handful of cycles per element of an HBM- or NVLink-bound stage).
+// OP_GRAD multiplies by i * w, everything else by w.
+ACC_HD_NOINLINE double op_weight(const StageDesc& d, const OpCol& c, int k) {
+  if (d.op == OP_SCALE) return d.scale;
   if (d.op == OP_GRAD) {
     // The reference differentiates with a REAL transform along the axis (src/operators_gpu.txx:172-278), i.e. it
     // only ever sees X <= N/2 and c2r implies the mirrored half: the mode pair +-floor(N/2) is zeroed as a pair.
-    // On a full (c2c) axis that means X == N/2 and X == N - N/2 (the same index when N is even).
-    const int ax = d.opAxis;
-    const int X = freq_index(d, ax, k, a, b), N = d.n[ax];
-    const double w = (X == N - N / 2 && !d.opFullAxis) ? 0.0 : d.scale * (double)wave_number(X, N);
-    return {T(-w * v.y), T(w * v.x)};
+    // On a full (c2c) axis that means X == N/2 and X == N - N/2 (the same index when N is even); the reference's full
+    // 3-D scheme (opFullAxis) zeroes X == N/2 only (src/operators_cuda.cu:34-37).
+    if (d.kind[d.opAxis] != 0) return c.g_fixed;
+    const int X = k + d.off[c.kax], N = d.n[c.kax];
+    return (X == N - N / 2 && !d.opFullAxis) ? 0.0 : d.scale * (double)wave_number(X, N);
   }
-  long long wx, wy, wz;
-  if (d.op == OP_INV_BIHARMONIC) {   // plain signed wave numbers: X == N/2 keeps N/2
-    const int X = freq_index(d, 0, k, a, b), Y = freq_index(d, 1, k, a, b), Z = freq_index(d, 2, k, a, b);
-    wx = X > d.n[0] / 2 ? X - d.n[0] : X;
-    wy = Y > d.n[1] / 2 ? Y - d.n[1] : Y;
-    wz = Z > d.n[2] / 2 ? Z - d.n[2] : Z;
-  } else {
-    wx = wave_number(freq_index(d, 0, k, a, b), d.n[0]);
-    wy = wave_number(freq_index(d, 1, k, a, b), d.n[1]);
-    wz = wave_number(freq_index(d, 2, k, a, b), d.n[2]);
-  }
-  const double s2 = (double)(wx * wx + wy * wy + wz * wz);
+  const int X = k + d.off[c.kax], N = d.n[c.kax];
+  const long long wk = d.op == OP_INV_BIHARMONIC ? wave_number_plain(X, N) : wave_number(X, N);
+  const double s2 = c.s_other + (double)(wk * wk);
   double w;
   switch (d.op) {
     case OP_LAPLACE: w = -s2; break;
     case OP_BIHARMONIC: w = s2 * s2; break;
     case OP_INV_LAPLACE: w = s2 == 0.0 ? 0.0 : -1.0 / s2; break;
-    case OP_INV_BIHARMONIC: w = s2 == 0.0 ? 1.0 : 1.0 / (s2 * s2); break;
+    case OP_INV_BIHARMONIC: w = s2 == 0.0 ? 1.0 : 1.0 / (s2 * s2); break;   // zero mode passed through (:379-381)
     case OP_SYMBOL_LIN: w = d.opA + d.opB * s2; break;
     default: {
       const double den = d.opA + d.opB * s2;
       w = den == 0.0 ? 0.0 : 1.0 / den;
     }
   }
-  w *= d.scale;
+  return w * d.scale;
+}
+
+template <class T>
+ACC_HD cplx<T> apply_op(const StageDesc& d, const OpCol& c, cplx<T> v, int k) {
+  if (d.op == OP_NONE) return v;
+  const double w = op_weight(d, c, k);
+  if (d.op == OP_GRAD) return {T(-w * v.y), T(w * v.x)};
   return {T(w * v.x), T(w * v.y)};
 }
 
-// the symbol multiply itself is out of line (apply_op_impl); stages without an operator never make the call
+// one-off form (copy stages, generic kernel): prepare + apply
 template <class T>
 ACC_HD cplx<T> apply_op(const StageDesc& d, cplx<T> v, int k, int a, int b) {
-  return d.op == OP_NONE ? v : apply_op_impl(d, v, k, a, b);
+  if (d.op == OP_NONE) return v;
+  const OpCol c = op_prepare(d, a, b);
+  return apply_op(d, c, v, k);
 }
 
 // true when the stage needs none of the generic machinery: one destination segment, no spectral operator
@@ -159,14 +200,25 @@ ACC_HD bool stage_is_simple(const StageDesc& d) { return d.nseg == 1 && d.op == 
 template <class T>
 ACC_HD cplx<T> cswap_if(cplx<T> a, bool sw) { return sw ? cplx<T>{a.y, a.x} : a; }
 
-// generic (segmented / operator) store of output element k of column (a, b)
+// generic (segmented / operator) store of output element k of column (a, b); col = op_prepare(d, a, b)
 template <class T>
-ACC_HD void store_generic(const StageDesc& d, cplx<T> y, int k, int a, int b) {
+ACC_HD void store_generic(const StageDesc& d, const OpCol& col, cplx<T> y, int k, int a, int b) {
   const int s = seg_of(d, k);
   const SegDst& sd = d.seg[s];
   cplx<T>* dst = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB +
                  (long long)(k - s * d.blk) * sd.strideI;
-  store_out(d, dst, d.opOnLoad ? y : apply_op(d, y, k, a, b));
+  store_out(d, dst, d.opOnLoad ? y : apply_op(d, col, y, k));
+}
+template <class T>
+ACC_HD void store_generic(const StageDesc& d, cplx<T> y, int k, int a, int b) {
+  OpCol col = {0.0, 0.0, 0};
+  if (d.op != OP_NONE && !d.opOnLoad) col = op_prepare(d, a, b);
+  store_generic(d, col, y, k, a, b);
+}
+ACC_HD OpCol op_prepare_if(const StageDesc& d, int a, int b) {
+  OpCol col = {0.0, 0.0, 0};
+  if (d.op != OP_NONE) col = op_prepare(d, a, b);
+  return col;
 }
 
 // ================================================================================================
@@ -187,6 +239,10 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
   const int b = (int)(tile % tpa) * TC + c - d.colShift;
   const bool valid = b >= 0 && b < d.nB;
   const bool inv = d.inv != 0;
+  OpCol col = {0.0, 0.0, 0};
+  if constexpr (GEN) {
+    if (valid) col = op_prepare_if(d, a, b);
+  }
   cplx<T> w1[S::NTW];
   load_base_twiddles<S, 1>(w1, t, (const cplx<T>*)d.tw);
   cplx<T> v[S::NREG];
@@ -206,7 +262,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
       }
     }
     if constexpr (GEN) {
-      if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = apply_op(d, r, i, a, b); });
+      if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = apply_op(d, col, r, i); });
     }
     if (inv) {
       ACC_UNROLL
@@ -235,7 +291,127 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
         }
       }
     } else {
-      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, r, k, a, b); });
+      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, col, r, k, a, b); });
+    }
+  }
+}
+
+
+// ================================================================================================
+// strided c2c, SINGLE precision, two adjacent columns per thread: the pair (b0, b0 + 1) travels as ONE 16-byte quantity
+// cplx<f2> = {re0, re1, im0, im1} through registers and shared memory, so that the kernel issues 128-bit global and
+// shared-memory accesses and half as many instructions per byte as the 8-byte-element form -- the same shape as the
+// double-precision kernel (TCP pair-columns = 128-byte row segments with G * TCP threads).  Twiddles stay scalar floats and
+// are shared by the two lanes.  A pair whose global address is not 16-byte aligned (odd row pitch on odd rows, odd column
+// shift) or that straddles the edge of the column range moves as two 8-byte halves; the choice is uniform per tile row.
+// ================================================================================================
+struct alignas(16) f4raw {
+  float x, y, z, w;
+};
+
+ACC_HD cplx<f2> load_pair(const cplx<float>* p, bool v0, bool v1) {
+  if (v0 && v1 && (((unsigned long long)p) & 15ull) == 0) {
+    const f4raw q = *reinterpret_cast<const f4raw*>(p);
+    return {f2(q.x, q.z), f2(q.y, q.w)};
+  }
+  const cplx<float> e0 = v0 ? ld_stream(p) : cplx<float>{0.f, 0.f};
+  const cplx<float> e1 = v1 ? ld_stream(p + 1) : cplx<float>{0.f, 0.f};
+  return {f2(e0.x, e1.x), f2(e0.y, e1.y)};
+}
+ACC_HD void store_pair(cplx<float>* p, cplx<f2> v, bool v0, bool v1) {
+  if (v0 && v1 && (((unsigned long long)p) & 15ull) == 0) {
+    *reinterpret_cast<f4raw*>(p) = f4raw{v.x.a, v.y.a, v.x.b, v.y.b};
+    return;
+  }
+  if (v0) st_stream(p, cplx<float>{v.x.a, v.y.a});
+  if (v1) st_stream(p + 1, cplx<float>{v.x.b, v.y.b});
+}
+
+template <class S, int TCP, bool GEN, class Ctx>
+ACC_HD void strided_c2c_pair_body(const StageDesc& d, Ctx& ctx) {
+  using T = f2;
+  constexpr int G = S::G;
+  constexpr int R0 = S::radix(0), NB0 = S::nb(0), CNT0 = S::cnt(0);
+  constexpr int RL = S::radix(S::NP - 1), NBL = S::nb(S::NP - 1), CNTL = S::cnt(S::NP - 1);
+  const int tid = ctx.tid();
+  const int c = tid % TCP, t = tid / TCP;
+  const int tpa = (d.nB + d.colShift + 2 * TCP - 1) / (2 * TCP);
+  const long long tile = ctx.bid();
+  const int a = (int)(tile / tpa);
+  const int b0 = 2 * ((int)(tile % tpa) * TCP + c) - d.colShift;
+  const bool v0 = b0 >= 0 && b0 < d.nB, v1 = b0 + 1 >= 0 && b0 + 1 < d.nB;
+  const bool inv = d.inv != 0;
+  OpCol col0 = {0.0, 0.0, 0}, col1 = {0.0, 0.0, 0};
+  if constexpr (GEN) {
+    if (v0) col0 = op_prepare_if(d, a, b0);
+    if (v1) col1 = op_prepare_if(d, a, b0 + 1);
+  }
+  cplx<float> w1[S::NTW];
+  load_base_twiddles<S, 1>(w1, t, (const cplx<float>*)d.tw);
+  cplx<T> v[S::NREG];
+  ACC_UNROLL
+  for (int i = 0; i < S::NREG; ++i) v[i] = {T(0.f), T(0.f)};
+  if (v0 || v1) {
+    const cplx<float>* in = (const cplx<float>*)d.in + (long long)a * d.inStrideA + b0;
+    const long long si = d.inStrideI;
+    const long long step = (long long)NB0 * si;
+    ACC_UNROLL
+    for (int u = 0; u < CNT0; ++u) {
+      const int j = t + u * G;
+      if (CNT0 * G == NB0 || j < NB0) {
+        const cplx<float>* p = in + (long long)j * si;
+        ACC_UNROLL
+        for (int r = 0; r < R0; ++r) v[u * R0 + r] = load_pair(p + r * step, v0, v1);
+      }
+    }
+    if constexpr (GEN) {
+      if (d.opOnLoad)
+        pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) {
+          const cplx<float> e0 = apply_op(d, col0, cplx<float>{r.x.a, r.y.a}, i);
+          const cplx<float> e1 = apply_op(d, col1, cplx<float>{r.x.b, r.y.b}, i);
+          r = {f2(e0.x, e1.x), f2(e0.y, e1.y)};
+        });
+    }
+    if (inv) {
+      ACC_UNROLL
+      for (int i = 0; i < S::NREG; ++i) v[i] = cswap(v[i]);
+    }
+  }
+  cplx<T>* sm = (cplx<T>*)ctx.smem();
+  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i) * TCP + c; }, [&]() { ctx.sync(); });
+  if (v0 || v1) {
+    if (inv) {
+      ACC_UNROLL
+      for (int i = 0; i < S::NREG; ++i) v[i] = cswap(v[i]);
+    }
+    if constexpr (!GEN) {
+      const SegDst& sd = d.seg[0];
+      cplx<float>* out = (cplx<float>*)sd.base + (long long)a * sd.strideA + (long long)b0 * sd.strideB;
+      const long long so = sd.strideI;
+      const long long step = (long long)NBL * so;
+      const bool unit = sd.strideB == 1;
+      ACC_UNROLL
+      for (int u = 0; u < CNTL; ++u) {
+        const int j = t + u * G;
+        if (CNTL * G == NBL || j < NBL) {
+          cplx<float>* p = out + (long long)j * so;
+          ACC_UNROLL
+          for (int r = 0; r < RL; ++r) {
+            const cplx<T> y = v[u * RL + r];
+            if (unit) {
+              store_pair(p + r * step, y, v0, v1);
+            } else {
+              if (v0) st_stream(p + r * step, cplx<float>{y.x.a, y.y.a});
+              if (v1) st_stream(p + r * step + sd.strideB, cplx<float>{y.x.b, y.y.b});
+            }
+          }
+        }
+      }
+    } else {
+      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) {
+        if (v0) store_generic(d, col0, cplx<float>{r.x.a, r.y.a}, k, a, b0);
+        if (v1) store_generic(d, col1, cplx<float>{r.x.b, r.y.b}, k, a, b0 + 1);
+      });
     }
   }
 }
@@ -326,7 +502,8 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
       if (d.staged) {
         pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { stage[staged_index<PC>(d, S::N, pcl, k)] = cswap_if(r, inv); });
       } else {
-        pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, cswap_if(r, inv), k, a, b); });
+        const OpCol col = op_prepare_if(d, a, b);
+        pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, col, cswap_if(r, inv), k, a, b); });
       }
     }
     if (d.staged) staged_flush<T, PC>(d, ctx, stage, S::N, ctx.bid() * PC, S::G * PC);
@@ -373,12 +550,14 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
     const SegDst& s0 = d.seg[0];
     cplx<T>* out0 = (cplx<T>*)s0.base + (long long)a * s0.strideA + (long long)b * s0.strideB;
     const long long so = s0.strideI;
+    OpCol col = {0.0, 0.0, 0};
+    if constexpr (GEN) col = op_prepare_if(d, a, b);
     auto put = [&](int kk, cplx<T> y) {
       if constexpr (!GEN) {
         st_stream(out0 + (long long)kk * so, y);
       } else {
         if (d.staged) stage[staged_index<PC>(d, M + 1, pcl, kk)] = y;
-        else store_generic(d, y, kk, a, b);
+        else store_generic(d, col, y, kk, a, b);
       }
     };
     // split step X[k] = (E + W_N2^k O)/2 for k = j + r*NBL:  W_N2^k = W_N2^j * W_(2 RL)^r, the second factor a
@@ -449,10 +628,11 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
       }
       if constexpr (GEN) {
         if (d.op != OP_NONE) {
+          const OpCol col = op_prepare(d, a, b);
           ACC_UNROLL
           for (int q = 0; q < NLD; ++q) {
             const int i = t + q * S::G;
-            if (i <= M) x[q] = apply_op(d, x[q], i, a, b);
+            if (i <= M) x[q] = apply_op(d, col, x[q], i);
           }
         }
       }

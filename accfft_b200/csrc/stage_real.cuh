@@ -128,6 +128,7 @@ ACC_HD void strided_c2r_body(const StageDesc& d, Ctx& ctx) {
   if (valid0) {
     const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b0 * d.inStrideB;
     const long long si = d.inStrideI;
+    const OpCol cola = op_prepare_if(d, a, b0), colb = op_prepare_if(d, a, b0 + 1);
     pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) {
       const bool lower = 2 * i <= N;
       const int m = lower ? i : N - i;
@@ -135,8 +136,8 @@ ACC_HD void strided_c2r_body(const StageDesc& d, Ctx& ctx) {
       cplx<T> xa = p[0];
       cplx<T> xb = valid1 ? p[d.inStrideB] : cplx<T>{T(0), T(0)};
       if (d.op != OP_NONE) {
-        xa = apply_op(d, xa, m, a, b0);
-        xb = apply_op(d, xb, m, a, b0 + 1);
+        xa = apply_op(d, cola, xa, m);
+        xb = apply_op(d, colb, xb, m);
       }
       if (m == 0 || 2 * m == N) xa.y = T(0), xb.y = T(0);
       // Z[i] = X_a + i X_b  (i <= N/2),  conj X_a + i conj X_b  (mirror);  stored swapped: inverse = swap.forward.swap
@@ -173,16 +174,17 @@ ACC_HD void strided_deriv_body(const StageDesc& d, Ctx& ctx) {
   cplx<T>* sm = (cplx<T>*)ctx.smem();
   auto addr = [&](int i) { return sm + S::phys(i) * TC + c; };
   fft_passes<S>(v, t, w1, addr, [&]() { ctx.sync(); });
+  const OpCol col = op_prepare_if(d, a, b0);   // (the derivative runs along the transform axis: nothing column dependent)
   // symbol multiply in output order (index j + r*N/R_last).  When the first and the last radix agree that IS the pass-0
   // gather order of the inverse (index j + r*N/R_0), so the registers go straight into the second set of passes;
   // otherwise they are re-ordered through the tile.  (swapped: inverse = swap . forward . swap)
   constexpr bool kSameOrder = S::radix(0) == S::radix(S::NP - 1);
   if constexpr (kSameOrder) {
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(apply_op(d, r, k, a, b0)); });
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(apply_op(d, col, r, k)); });
     if constexpr (S::NP > 1) ctx.sync();   // the forward's last gathers are done before the inverse scatters again
   } else {
     if constexpr (S::NP > 1) ctx.sync();
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(apply_op(d, r, k, a, b0)); });
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(apply_op(d, col, r, k)); });
     ctx.sync();
     pass_gather<S, 0>(v, t, addr);
     if constexpr (S::NP > 1) ctx.sync();
@@ -221,13 +223,14 @@ ACC_HD void contig_deriv_body(const StageDesc& d, Ctx& ctx) {
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   auto addr = [&](int i) { return sm + S::phys(i); };
   fft_passes<S>(v, t, w1, addr, [&]() { ctx.sync(); });
+  const OpCol col = op_prepare_if(d, a0, b0);
   constexpr bool kSameOrder = S::radix(0) == S::radix(S::NP - 1);
   if constexpr (kSameOrder) {
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(apply_op(d, r, k, a0, b0)); });
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(apply_op(d, col, r, k)); });
     if constexpr (S::NP > 1) ctx.sync();
   } else {
     if constexpr (S::NP > 1) ctx.sync();
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(apply_op(d, r, k, a0, b0)); });
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(apply_op(d, col, r, k)); });
     ctx.sync();
     pass_gather<S, 0>(v, t, addr);
     if constexpr (S::NP > 1) ctx.sync();

@@ -205,8 +205,10 @@ __global__ void __launch_bounds__(TmaCfg<T, S, TC>::THREADS, TmaCfg<T, S, TC>::C
         for (int r = 0; r < R0; ++r) v[u * R0 + r] = sm[(j + r * NB0) * TC + c];
       }
     }
+    OpCol col = {0.0, 0.0, 0};
     if constexpr (GEN) {
-      if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int k, cplx<T>& r) { r = apply_op(d, r, k, a, b); });
+      if (valid) col = op_prepare_if(d, a, b);
+      if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int k, cplx<T>& r) { r = apply_op(d, col, r, k); });
     }
     if (inv) {
 #pragma unroll
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(TmaCfg<T, S, TC>::THREADS, TmaCfg<T, S, TC>::C
           }
         }
       } else {
-        pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, r, k, a, b); });
+        pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, col, r, k, a, b); });
       }
     }
   }

@@ -76,8 +76,8 @@ int accfftb_stage_size(const int n[3], const int c_dims[2], const int coords[2],
 
 /* Transform lengths.  Like the reference (which hands any length to cuFFT, src/accfft_gpu.cpp:173-253) every length plans:
  *   accfftb_length_fast(n)       1 if a compiled Stockham schedule exists for the complex length n: 2^a 3^b 5^c <= 2048
- *                                (b, c <= 3), the same with one extra factor 7 / 11 / 13 / 49, and 4096.  The r2c / c2r Z pass
- *                                runs the N2/2-point schedule and therefore needs N2 even with N2/2 fast.
+ *                                (b, c <= 3); 7 * 2^a 3^b 5^c (b, c <= 1); 11 / 13 / 49 times a power of two; 4096.  The
+ *                                r2c / c2r Z pass runs the N2/2-point schedule: it needs N2 even with N2/2 fast.
  *   accfftb_length_supported(n)  1 if an axis of length n can be planned at all: fast, or through the generic O(n^2) stage
  *                                kernel (any n up to 7168; also serves odd N2 in r2c plans).  That kernel is a correctness
  *                                fallback for the odd axis of an awkward grid, not a fast path.

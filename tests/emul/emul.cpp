@@ -115,6 +115,10 @@ struct EmuBackend : Backend {
     const char* c = getenv("EMU_PIPELINE_CHUNKS");
     return c ? atoi(c) : 1;
   }
+  int l2_planes(const Plan&) override {
+    const char* c = getenv("EMU_L2_PLANES");
+    return c ? atoi(c) : 0;
+  }
   // copy-engine exchange (Plan::forward_slab_ce / inverse_slab_ce): copies are row memcpys executed in program order
   std::vector<char> stage_buf;
   int ce_chunks() override {
@@ -139,7 +143,7 @@ struct EmuWorld {
   Prec prec;
   std::vector<EmuBackend> be;
   std::vector<Plan> plans;
-  std::vector<std::vector<char>> bufA, bufB, spec;
+  std::vector<std::vector<char>> bufA, bufB, bufA2, bufB2, spec;
   pthread_barrier_t bar;
 };
 int EmuBackend::barrier() {
@@ -161,6 +165,8 @@ void* emu_world_create(const int* n, int P0, int P1, int r2c, int prec) {
   w->plans.resize(w->nprocs);
   w->bufA.resize(w->nprocs);
   w->bufB.resize(w->nprocs);
+  w->bufA2.resize(w->nprocs);
+  w->bufB2.resize(w->nprocs);
   w->spec.resize(w->nprocs);
   pthread_barrier_init(&w->bar, nullptr, w->nprocs);
   const int sz = prec == PREC_DOUBLE ? 8 : 4;
@@ -177,14 +183,22 @@ void* emu_world_create(const int* n, int P0, int P1, int r2c, int prec) {
     const size_t bb = (size_t)Plan::buffer_bytes(w->n, w->np, coords, w->r2c, w->prec, w->nprocs);
     w->bufA[r].assign(bb + 64, (char)0xEE);
     w->bufB[r].assign(bb + 64, (char)0xEE);
+    w->bufA2[r].assign(bb + 64, (char)0xEE);
+    w->bufB2[r].assign(bb + 64, (char)0xEE);
     w->spec[r].assign(bb + 64, (char)0xEE);
     w->be[r].stage_buf.assign(bb + 64, (char)0xEE);
   }
   for (int r = 0; r < w->nprocs; ++r) {
     Plan& p = w->plans[r];
+    const char* dbenv = getenv("EMU_DB");   // double-buffered exchange buffers (plan.hpp: flip): on unless EMU_DB=0
+    const bool dbuf = w->nprocs > 1 && !(dbenv && dbenv[0] == '0');
     for (int q = 0; q < w->nprocs; ++q) {
       p.peerA.push_back(w->bufA[q].data());
       p.peerB.push_back(w->bufB[q].data());
+      if (dbuf) {
+        p.peerA_alt.push_back(w->bufA2[q].data());
+        p.peerB_alt.push_back(w->bufB2[q].data());
+      }
     }
     if (!p.check_supported()) {
       fprintf(stderr, "emul: %s\n", p.error.c_str());
@@ -208,6 +222,8 @@ static int canaries_ok(EmuWorld* w) {
     for (int i = 0; i < 64; ++i) {
       if ((unsigned char)w->bufA[r][w->bufA[r].size() - 64 + i] != 0xEE) return 0;
       if ((unsigned char)w->bufB[r][w->bufB[r].size() - 64 + i] != 0xEE) return 0;
+      if ((unsigned char)w->bufA2[r][w->bufA2[r].size() - 64 + i] != 0xEE) return 0;
+      if ((unsigned char)w->bufB2[r][w->bufB2[r].size() - 64 + i] != 0xEE) return 0;
     }
   return 1;
 }

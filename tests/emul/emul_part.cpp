@@ -17,6 +17,17 @@ static void emu_launch_sched(const Launch& l) {
   const bool gen = !stage_is_simple(d);   // the same choice the CUDA launchers make (launch_impl.cuh: launch_pair)
   switch (l.kind) {
     case K_STRIDED_C2C: {
+      if constexpr (sizeof(T) == 4) {   // single precision: the pair kernel, as in launch_impl.cuh
+        using PC = PairCfg<S>;
+        if (d.inStrideB == 1) {
+          const long long nbp = (long long)d.nA * ((d.nB + d.colShift + 2 * PC::TCP - 1) / (2 * PC::TCP));
+          run_grid(nbp, PC::THREADS, PC::SMEM, [&](EmuCtx& c) {
+            if (gen) strided_c2c_pair_body<S, PC::TCP, true>(d, c);
+            else strided_c2c_pair_body<S, PC::TCP, false>(d, c);
+          });
+          break;
+        }
+      }
       const long long nb = (long long)d.nA * ((d.nB + d.colShift + C::TC - 1) / C::TC);
       run_grid(nb, C::STRIDED_THREADS, C::STRIDED_SMEM, [&](EmuCtx& c) {
         if (gen) strided_c2c_body<T, S, C::TC, true>(d, c);

@@ -289,3 +289,19 @@ def test_radix_7_11_13_lengths(n, np_):
     assert orc.rel_l2(orc.assemble_output(w.forward(z), n, np_, r2c=False), Z) < 1e-12
     assert orc.rel_l2(orc.assemble_input(w.inverse(Z), n, np_), z * z.size) < 1e-12
     w.close()
+
+
+@pytest.mark.parametrize("planes", [1, 3, 5])
+@pytest.mark.parametrize("n,r2c", [((16, 12, 20), True), ((7, 10, 16), True), ((12, 8, 6), False)])
+def test_l2_chunked_local_passes(monkeypatch, n, r2c, planes):
+    """Plan::forward_zy_l2 / inverse_yz_l2: Z and Y chunk by chunk over i0 through the reused head of A / B (single rank)"""
+    monkeypatch.setenv("EMU_L2_PLANES", str(planes))
+    x = orc.synthetic_real(n, 5) if r2c else orc.synthetic_complex(n, 5)
+    X = orc.forward_r2c(x) if r2c else orc.forward_c2c(x)
+    w = emu.World(n, (1, 1), r2c=r2c)
+    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, (1, 1), r2c=r2c), X) < 1e-12
+    assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, (1, 1)), x * x.size) < 1e-12
+    if r2c:
+        assert orc.rel_l2(orc.assemble_output(w.forward(x, padded=True), n, (1, 1)), X) < 1e-12
+        assert orc.rel_l2(orc.assemble_input(w.inverse(X, padded=True), n, (1, 1)), x * x.size) < 1e-12
+    w.close()
