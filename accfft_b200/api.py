@@ -74,6 +74,7 @@ def lib():
     L.accfftb_plan_set_profiling.argtypes = [c_vp, c_int]
     L.accfftb_plan_profile_read.argtypes = [c_vp, c_dp, ctypes.POINTER(c_ll)]
     L.accfftb_plan_stage_variant.argtypes = [c_vp, c_int]
+    L.accfftb_plan_fused_info.argtypes = [c_vp, c_int, ip]
     L.accfftb_plan_alloc_max.restype = c_ll
     L.accfftb_plan_alloc_max.argtypes = [c_vp]
     L.accfftb_plan_launch_count.restype = c_ll
@@ -284,6 +285,15 @@ class Plan:
         """-> {stage: "plain" | "tma" | "heuristic"} for the four strided stages (see accfftb_plan_stage_variant)"""
         names = {0: "heuristic", 1: "plain", 2: "tma", 3: "wide"}
         return {self.PROFILE_SLOTS[s]: names.get(lib().accfftb_plan_stage_variant(self._h, s), "?") for s in (1, 2, 3, 4)}
+
+    def fused_info(self, inverse: bool = False):
+        """accfftb_plan_fused_info: None if the last transform in that direction ran its local Z / Y passes as two kernels, else
+        what the fused persistent kernel used: {"cp", "lag", "ns", "chunks", "ring_planes", "grid", "threads", "smem"}"""
+        arr = (ctypes.c_int * 8)()
+        r = lib().accfftb_plan_fused_info(self._h, 1 if inverse else 0, arr)
+        if r != 1:
+            return None
+        return dict(zip(("cp", "lag", "ns", "chunks", "ring_planes", "grid", "threads", "smem"), [int(v) for v in arr]))
 
     @property
     def launch_count(self) -> int:

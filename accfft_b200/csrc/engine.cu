@@ -18,6 +18,7 @@
 #include "../../include/accfft_b200.h"
 #include "plan.hpp"
 #include "kernel_cfg.hpp"
+#include "fused_launch.hpp"
 
 namespace accfft_b200 {
 
@@ -275,6 +276,7 @@ struct CudaBackend : Backend {
   int local_variant(const Launch& l) override;
   int l2_planes(const Plan& p) override;
   int l2_window(const void* ptr, size_t bytes) override;
+  int launch_fused(const Launch& lz, const Launch& ly, bool z_first) override;
 };
 
 constexpr size_t kFlagBytes = 4096;
@@ -296,6 +298,12 @@ struct Engine {
   bool l2_persist = false;     // ACCFFT_B200_L2_PERSIST=1: give the hand-off buffer an L2-persisting access-policy window
   size_t l2_window_max = 0;
   long long l2_budget = 0;     // ACCFFT_B200_L2_MB: bytes of intermediate planes kept L2-resident between two local passes (0: off)
+  // fused local Z / Y pair (fused.cuh): ACCFFT_B200_FUSED=0 switches it off; _CP / _LAG / _NS / _HINTS tune it
+  int fused_mode = 1;
+  FusedTune fused_tune = {0, 0, 0, 1};
+  FusedInfo fused_info[2] = {};   // what the last forward / inverse fused launch used (accfftb_plan_fused_info)
+  int* fused_ctr = nullptr;
+  static constexpr int kFusedCtrInts = 16384;
   int push_ctas = 0;           // ACCFFT_B200_PUSH: CTAs of the TMA push kernel per transfer (0: copy engines / cudaMemcpyAsync)
   cudaStream_t copy_streams[kMaxCopyLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* stage_buf = nullptr;   // local staging buffer of the exchanging stage (one exchange buffer long)
@@ -605,6 +613,43 @@ int CudaBackend::launch(const Launch& l) {
   return 0;
 }
 
+// the local Z / Y pair as one persistent kernel (fused.cuh); -2 = not available for this pair, run the stages separately
+int CudaBackend::launch_fused(const Launch& lz, const Launch& ly, bool z_first) {
+  if (!lz.dry) e->fused_info[z_first ? 0 : 1] = FusedInfo{};
+  if (!e->fused_mode || !e->fused_ctr) return -2;
+  if (e->timing && !lz.dry) return -2;   // per-stage timers of the reference-style `timer` array want separate stages
+  const bool r2c = lz.kind == K_CONTIG_R2C || lz.kind == K_CONTIG_C2R;
+  if (!r2c && lz.kind != K_CONTIG_C2C) return -2;
+  if (ly.kind != K_STRIDED_C2C || lz.prec != ly.prec) return -2;
+  if (r2c && e->plan.g.n[2] % 2 != 0) return -2;
+  if (!length_supported(lz.fftN) || !length_supported(ly.fftN)) return -2;
+  if (!lz.desc.tw || !ly.desc.tw) return fail(ACCFFTB_ERR_STATE, "twiddle table allocation failed");
+  const bool dry = lz.dry;
+  const int mode = (r2c ? 0 : 2) + (z_first ? 0 : 1);
+  ScopedProfile pf(e, dry ? -1 : (z_first ? lz.slot : ly.slot));
+  FusedInfo* info = dry ? nullptr : &e->fused_info[z_first ? 0 : 1];
+  if (info) *info = FusedInfo{};
+  int rc = -2;
+  const int p = (int)lz.prec;
+  switch (mode * 2 + p) {
+    case 0: rc = accfft_launch_fused_m0_p0(lz, ly, e->fused_tune, e->fused_ctr, Engine::kFusedCtrInts, e->stream, dry, info); break;
+    case 1: rc = accfft_launch_fused_m0_p1(lz, ly, e->fused_tune, e->fused_ctr, Engine::kFusedCtrInts, e->stream, dry, info); break;
+    case 2: rc = accfft_launch_fused_m1_p0(lz, ly, e->fused_tune, e->fused_ctr, Engine::kFusedCtrInts, e->stream, dry, info); break;
+    case 3: rc = accfft_launch_fused_m1_p1(lz, ly, e->fused_tune, e->fused_ctr, Engine::kFusedCtrInts, e->stream, dry, info); break;
+    case 4: rc = accfft_launch_fused_m2_p0(lz, ly, e->fused_tune, e->fused_ctr, Engine::kFusedCtrInts, e->stream, dry, info); break;
+    case 5: rc = accfft_launch_fused_m2_p1(lz, ly, e->fused_tune, e->fused_ctr, Engine::kFusedCtrInts, e->stream, dry, info); break;
+    case 6: rc = accfft_launch_fused_m3_p0(lz, ly, e->fused_tune, e->fused_ctr, Engine::kFusedCtrInts, e->stream, dry, info); break;
+    default: rc = accfft_launch_fused_m3_p1(lz, ly, e->fused_tune, e->fused_ctr, Engine::kFusedCtrInts, e->stream, dry, info); break;
+  }
+  if (rc == -2) {
+    if (pf.on) e->pool.push_back(pf.r.a), e->pool.push_back(pf.r.b), pf.on = false;
+    return -2;
+  }
+  if (rc != 0) return cuda_fail((cudaError_t)rc, "fused stage kernel launch");
+  if (!dry) e->launches++;
+  return 0;
+}
+
 int CudaBackend::barrier() {
   if (!e->wired) return fail(ACCFFTB_ERR_STATE, "multi-rank plan used before its peers were attached");
   ScopedTimer tm(e, &e->t_bar);
@@ -656,6 +701,7 @@ static void engine_free(Engine* e) {
   if (e->spec) cudaFree(e->spec);
   if (e->status_h) cudaFreeHost(e->status_h);
   if (e->stage_buf) cudaFree(e->stage_buf);
+  if (e->fused_ctr) cudaFree(e->fused_ctr);
   for (auto& cs : e->copy_streams)
     if (cs) cudaStreamSynchronize(cs), cudaStreamDestroy(cs);
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
@@ -903,6 +949,12 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
       e->timeout_cycles = 10LL * 1000 * (long long)khz;   // 10 seconds of SM clock
     if (const char* m = getenv("ACCFFT_B200_BARRIER_TIMEOUT_MS")) e->timeout_cycles = (long long)atoll(m) * (long long)(khz > 0 ? khz : 2000000);
   }
+  if (const char* m = getenv("ACCFFT_B200_FUSED")) e->fused_mode = atoi(m);
+  if (const char* m = getenv("ACCFFT_B200_FUSED_CP")) e->fused_tune.cp = atoi(m);
+  if (const char* m = getenv("ACCFFT_B200_FUSED_LAG")) e->fused_tune.lag = atoi(m);
+  if (const char* m = getenv("ACCFFT_B200_FUSED_NS")) e->fused_tune.ns = atoi(m);
+  if (const char* m = getenv("ACCFFT_B200_FUSED_HINTS")) e->fused_tune.hints = atoi(m);
+  if (err == cudaSuccess && e->fused_mode && c_dims[1] == 1) err = cudaMalloc((void**)&e->fused_ctr, sizeof(int) * Engine::kFusedCtrInts);
   if (err == cudaSuccess) err = cudaEventCreate(&e->ev[0]);
   if (err == cudaSuccess) err = cudaEventCreate(&e->ev[1]);
   if (err == cudaSuccess) err = cudaDeviceSynchronize();
@@ -1106,6 +1158,16 @@ int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOT
 int accfftb_plan_stage_variant(const accfftb_plan* plan, int slot) {
   if (!plan || slot < 0 || slot >= ACCFFTB_PROFILE_SLOTS) return -1;
   return plan->e.variant[slot];
+}
+
+int accfftb_plan_fused_info(const accfftb_plan* plan, int dir, int info[8]) {
+  if (!plan || dir < 0 || dir > 1) return -1;
+  const FusedInfo& f = plan->e.fused_info[dir];
+  if (info) {
+    const int v[8] = {f.cp, f.lag, f.ns, f.nch, f.ring_planes, f.grid, f.threads, f.smem};
+    for (int i = 0; i < 8; ++i) info[i] = v[i];
+  }
+  return f.grid > 0 ? 1 : 0;
 }
 
 long long accfftb_plan_alloc_max(const accfftb_plan* plan) { return plan ? plan->e.plan.g.L.alloc_max : -1; }

@@ -354,6 +354,13 @@ int Plan::prepare() {
     l.dry = true;
     if (int rc = be->launch(l)) return rc;
   }
+  if (g.np[1] == 1) {   // fused local pair (both directions)
+    ls[0].dry = ls[1].dry = ls[4].dry = ls[5].dry = true;
+    int rc = be->launch_fused(ls[0], ls[1], true);
+    if (rc && rc != -2) return rc;
+    rc = be->launch_fused(ls[5], ls[4], false);
+    if (rc && rc != -2) return rc;
+  }
   Launch c = fwd_y();   // the no-transform stage of partial-axis executes
   no_transform(c, g.n[1]);
   c.dry = true;
@@ -654,6 +661,12 @@ int Plan::inverse_slab_ce(const void* in, void* out, bool out_padded) {
   return 0;
 }
 
+// Z and Y are both local to the rank when the row group has one member: try the fused kernel, else one after the other
+int Plan::fused_pair(const Launch& z, const Launch& y, bool z_first) {
+  if (g.np[1] != 1 || empty(z) || empty(y)) return -2;
+  return be->launch_fused(z, y, z_first);
+}
+
 int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
   int rc;
   flip();
@@ -672,12 +685,17 @@ int Plan::execute_forward(const void* in, void* out, bool in_padded, int xyz) {
     return 0;
   }
   Launch z = fwd_z(in, in_padded);
-  if (!(xyz & 4)) no_transform(z, g.n[2]);
-  if (!empty(z) && (rc = be->launch(z))) return rc;
-  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch y = fwd_y();
-  if (!(xyz & 2)) no_transform(y, g.n[1]);
-  if (!empty(y) && (rc = be->launch(y))) return rc;
+  rc = xyz == 7 ? fused_pair(z, y, true) : -2;
+  if (rc == -2) {
+    if (!(xyz & 4)) no_transform(z, g.n[2]);
+    if (!empty(z) && (rc = be->launch(z))) return rc;
+    if ((rc = bar_if(row_exchanges()))) return rc;
+    if (!(xyz & 2)) no_transform(y, g.n[1]);
+    if (!empty(y) && (rc = be->launch(y))) return rc;
+  } else if (rc) {
+    return rc;
+  }
   if ((rc = bar_if(col_exchanges()))) return rc;
   Launch x = fwd_x(out);
   if (!(xyz & 1)) no_transform(x, g.n[0]);
@@ -700,12 +718,17 @@ int Plan::execute_inverse(const void* in, void* out, bool out_padded, int xyz) {
   if (!empty(x) && (rc = be->launch(x))) return rc;
   if ((rc = bar_if(col_exchanges()))) return rc;
   Launch y = inv_y();
-  if (!(xyz & 2)) no_transform(y, g.n[1]);
-  if (!empty(y) && (rc = be->launch(y))) return rc;
-  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch z = inv_z(out, out_padded);
-  if (!(xyz & 4)) no_transform(z, g.n[2]);
-  if (!empty(z) && (rc = be->launch(z))) return rc;
+  rc = xyz == 7 ? fused_pair(z, y, false) : -2;
+  if (rc == -2) {
+    if (!(xyz & 2)) no_transform(y, g.n[1]);
+    if (!empty(y) && (rc = be->launch(y))) return rc;
+    if ((rc = bar_if(row_exchanges()))) return rc;
+    if (!(xyz & 4)) no_transform(z, g.n[2]);
+    if (!empty(z) && (rc = be->launch(z))) return rc;
+  } else if (rc) {
+    return rc;
+  }
   return 0;
 }
 
@@ -713,10 +736,14 @@ int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double
   int rc;
   flip();
   Launch z = fwd_z(in, false);
-  if (!empty(z) && (rc = be->launch(z))) return rc;
-  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch y = fwd_y();
-  if (!empty(y) && (rc = be->launch(y))) return rc;
+  if ((rc = fused_pair(z, y, true)) == -2) {
+    if (!empty(z) && (rc = be->launch(z))) return rc;
+    if ((rc = bar_if(row_exchanges()))) return rc;
+    if (!empty(y) && (rc = be->launch(y))) return rc;
+  } else if (rc) {
+    return rc;
+  }
   if ((rc = bar_if(col_exchanges()))) return rc;
   // X forward with the symbol multiply and the 1/N normalisation fused into its stores, into `spec`
   // (user spectrum layout), which the inverse X stage reads back
@@ -731,10 +758,14 @@ int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double
   if (!empty(xi) && (rc = be->launch(xi))) return rc;
   if ((rc = bar_if(col_exchanges()))) return rc;
   Launch yi = inv_y();
-  if (!empty(yi) && (rc = be->launch(yi))) return rc;
-  if ((rc = bar_if(row_exchanges()))) return rc;
   Launch zi = inv_z(out, false);
-  if (!empty(zi) && (rc = be->launch(zi))) return rc;
+  if ((rc = fused_pair(zi, yi, false)) == -2) {
+    if (!empty(yi) && (rc = be->launch(yi))) return rc;
+    if ((rc = bar_if(row_exchanges()))) return rc;
+    if (!empty(zi) && (rc = be->launch(zi))) return rc;
+  } else if (rc) {
+    return rc;
+  }
   return 0;
 }
 

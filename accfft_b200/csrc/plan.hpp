@@ -55,6 +55,10 @@ struct Backend {
   virtual int l2_planes(const struct Plan&) { return 0; }
   // mark [ptr, ptr + bytes) as the L2-persisting window of the stages launched from now on (bytes == 0: no window)
   virtual int l2_window(const void*, size_t) { return 0; }
+  // The two passes that are local on a 1 x 1 / slab grid (forward Z then Y, inverse Y then Z) as ONE persistent kernel whose
+  // intermediate stays in L2 (fused.cuh).  lz = the contiguous (Z) stage, ly = the strided (Y) stage; z_first = forward.
+  // Returns -2 when the backend has no fused kernel for the pair (the caller launches the two stages one after the other).
+  virtual int launch_fused(const Launch& /*lz*/, const Launch& /*ly*/, bool /*z_first*/) { return -2; }
 };
 
 struct Geometry {
@@ -152,6 +156,8 @@ struct Plan {
   int forward_zy_pipelined(const void* in, bool in_padded, int nch);
   // slab grids: exchange through a local staging buffer + copy-engine transfers, overlapped with the neighbouring stages
   bool use_ce(int xyz) { return xyz == 7 && nprocs > 1 && g.np[1] == 1 && be->ce_chunks() > 0 && be->staging() != nullptr; }
+  // the local Z / Y pair as one fused kernel when the backend has one for these lengths (rc -2: it does not)
+  int fused_pair(const Launch& z, const Launch& y, bool z_first);
   int forward_zy_l2(const void* in, bool in_padded, int planes);
   int inverse_yz_l2(void* out, bool out_padded, int planes);
   int forward_slab_ce(const void* in, void* out, bool in_padded);

@@ -70,7 +70,60 @@ struct StageDesc {
   int staged;            // contiguous kernels with nseg > 1: outputs are collected in shared memory per destination
                          // segment and leave the CTA as bulk (TMA) copies of whole runs -- full 128-byte lines on the
                          // NVLink wire instead of one partial-line packet per warp store.  Set by the launcher.
+  // Fused two-pass kernel (fused.cuh): the buffer between the two passes is used as a RING of a few planes of the outer
+  // index a (plane a lives at slot a % ring) that stays resident in L2, so the intermediate array never reaches HBM.
+  // Only honoured by kernels whose context says so (ctx_ring); 0 = plain addressing.
+  int inRing, outRing;
+  int ringHints;         // 1: accesses that do NOT touch the ring are marked evict-first (they stream through L2 once)
 };
+
+// does this execution context run ring-addressed stages (the fused persistent kernel)?  Default: no.
+template <class Ctx, class = void>
+struct ctx_ring : std::false_type {};
+template <class Ctx>
+struct ctx_ring<Ctx, std::void_t<decltype(Ctx::kRing)>> : std::integral_constant<bool, Ctx::kRing> {};
+
+template <class Ctx> ACC_HD int ring_in(const StageDesc& d, int a) {
+  if constexpr (ctx_ring<Ctx>::value) return d.inRing ? a % d.inRing : a;
+  else return a;
+}
+template <class Ctx> ACC_HD int ring_out(const StageDesc& d, int a) {
+  if constexpr (ctx_ring<Ctx>::value) return d.outRing ? a % d.outRing : a;
+  else return a;
+}
+
+// global loads / stores of a stage.  In a ring context, ring data is read with ld.global.cg (L2 only: another SM wrote it
+// during this kernel, an L1 line could be stale) and everything else may carry an evict-first hint.
+template <class Ctx, class T>
+ACC_HD cplx<T> ld_g(const StageDesc& d, const cplx<T>* p) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (ctx_ring<Ctx>::value) {
+    if constexpr (sizeof(T) == 8) {
+      const double2 v = d.inRing ? __ldcg(reinterpret_cast<const double2*>(p))
+                                 : (d.ringHints ? __ldcs(reinterpret_cast<const double2*>(p)) : *reinterpret_cast<const double2*>(p));
+      return {v.x, v.y};
+    } else {
+      const float2 v = d.inRing ? __ldcg(reinterpret_cast<const float2*>(p))
+                                : (d.ringHints ? __ldcs(reinterpret_cast<const float2*>(p)) : *reinterpret_cast<const float2*>(p));
+      return {v.x, v.y};
+    }
+  }
+#endif
+  return ld_stream(p);
+}
+template <class Ctx, class T>
+ACC_HD void st_g(const StageDesc& d, cplx<T>* p, cplx<T> v) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (ctx_ring<Ctx>::value) {
+    if (!d.outRing && d.ringHints) {
+      if constexpr (sizeof(T) == 8) __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+      else __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+      return;
+    }
+  }
+#endif
+  st_stream(p, v);
+}
 
 template <class T>
 ACC_HD void store_out(const StageDesc& d, cplx<T>* dst, cplx<T> y) {
@@ -249,7 +302,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
   if (valid) {
-    const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + b;
+    const cplx<T>* in = (const cplx<T>*)d.in + (long long)ring_in<Ctx>(d, a) * d.inStrideA + b;
     const long long si = d.inStrideI;
     const long long step = (long long)NB0 * si;
     ACC_UNROLL
@@ -258,7 +311,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
       if (CNT0 * G == NB0 || j < NB0) {
         const cplx<T>* p = in + (long long)j * si;
         ACC_UNROLL
-        for (int r = 0; r < R0; ++r) v[u * R0 + r] = ld_stream(p + r * step);
+        for (int r = 0; r < R0; ++r) v[u * R0 + r] = ld_g<Ctx>(d, p + r * step);
       }
     }
     if constexpr (GEN) {
@@ -278,7 +331,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
     }
     if constexpr (!GEN) {
       const SegDst& sd = d.seg[0];
-      cplx<T>* out = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
+      cplx<T>* out = (cplx<T>*)sd.base + (long long)ring_out<Ctx>(d, a) * sd.strideA + (long long)b * sd.strideB;
       const long long so = sd.strideI;
       const long long step = (long long)NBL * so;
       ACC_UNROLL
@@ -287,11 +340,12 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
         if (CNTL * G == NBL || j < NBL) {
           cplx<T>* p = out + (long long)j * so;
           ACC_UNROLL
-          for (int r = 0; r < RL; ++r) st_stream(p + r * step, v[u * RL + r]);
+          for (int r = 0; r < RL; ++r) st_g<Ctx>(d, p + r * step, v[u * RL + r]);
         }
       }
     } else {
-      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, col, r, k, a, b); });
+      const int ao = ring_out<Ctx>(d, a);
+      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { store_generic(d, col, r, k, ao, b); });
     }
   }
 }
@@ -309,22 +363,39 @@ struct alignas(16) f4raw {
   float x, y, z, w;
 };
 
-ACC_HD cplx<f2> load_pair(const cplx<float>* p, bool v0, bool v1) {
+template <class Ctx>
+ACC_HD cplx<f2> load_pair(const StageDesc& d, const cplx<float>* p, bool v0, bool v1) {
   if (v0 && v1 && (((unsigned long long)p) & 15ull) == 0) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (ctx_ring<Ctx>::value) {
+      const float4 q = d.inRing ? __ldcg(reinterpret_cast<const float4*>(p))
+                                : (d.ringHints ? __ldcs(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p));
+      return {f2(q.x, q.z), f2(q.y, q.w)};
+    }
+#endif
     const f4raw q = *reinterpret_cast<const f4raw*>(p);
     return {f2(q.x, q.z), f2(q.y, q.w)};
   }
-  const cplx<float> e0 = v0 ? ld_stream(p) : cplx<float>{0.f, 0.f};
-  const cplx<float> e1 = v1 ? ld_stream(p + 1) : cplx<float>{0.f, 0.f};
+  const cplx<float> e0 = v0 ? ld_g<Ctx>(d, p) : cplx<float>{0.f, 0.f};
+  const cplx<float> e1 = v1 ? ld_g<Ctx>(d, p + 1) : cplx<float>{0.f, 0.f};
   return {f2(e0.x, e1.x), f2(e0.y, e1.y)};
 }
-ACC_HD void store_pair(cplx<float>* p, cplx<f2> v, bool v0, bool v1) {
+template <class Ctx>
+ACC_HD void store_pair(const StageDesc& d, cplx<float>* p, cplx<f2> v, bool v0, bool v1) {
   if (v0 && v1 && (((unsigned long long)p) & 15ull) == 0) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (ctx_ring<Ctx>::value) {
+      if (!d.outRing && d.ringHints) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v.x.a, v.y.a, v.x.b, v.y.b));
+        return;
+      }
+    }
+#endif
     *reinterpret_cast<f4raw*>(p) = f4raw{v.x.a, v.y.a, v.x.b, v.y.b};
     return;
   }
-  if (v0) st_stream(p, cplx<float>{v.x.a, v.y.a});
-  if (v1) st_stream(p + 1, cplx<float>{v.x.b, v.y.b});
+  if (v0) st_g<Ctx>(d, p, cplx<float>{v.x.a, v.y.a});
+  if (v1) st_g<Ctx>(d, p + 1, cplx<float>{v.x.b, v.y.b});
 }
 
 template <class S, int TCP, bool GEN, class Ctx>
@@ -352,7 +423,7 @@ ACC_HD void strided_c2c_pair_body(const StageDesc& d, Ctx& ctx) {
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0.f), T(0.f)};
   if (v0 || v1) {
-    const cplx<float>* in = (const cplx<float>*)d.in + (long long)a * d.inStrideA + b0;
+    const cplx<float>* in = (const cplx<float>*)d.in + (long long)ring_in<Ctx>(d, a) * d.inStrideA + b0;
     const long long si = d.inStrideI;
     const long long step = (long long)NB0 * si;
     ACC_UNROLL
@@ -361,7 +432,7 @@ ACC_HD void strided_c2c_pair_body(const StageDesc& d, Ctx& ctx) {
       if (CNT0 * G == NB0 || j < NB0) {
         const cplx<float>* p = in + (long long)j * si;
         ACC_UNROLL
-        for (int r = 0; r < R0; ++r) v[u * R0 + r] = load_pair(p + r * step, v0, v1);
+        for (int r = 0; r < R0; ++r) v[u * R0 + r] = load_pair<Ctx>(d, p + r * step, v0, v1);
       }
     }
     if constexpr (GEN) {
@@ -386,7 +457,7 @@ ACC_HD void strided_c2c_pair_body(const StageDesc& d, Ctx& ctx) {
     }
     if constexpr (!GEN) {
       const SegDst& sd = d.seg[0];
-      cplx<float>* out = (cplx<float>*)sd.base + (long long)a * sd.strideA + (long long)b0 * sd.strideB;
+      cplx<float>* out = (cplx<float>*)sd.base + (long long)ring_out<Ctx>(d, a) * sd.strideA + (long long)b0 * sd.strideB;
       const long long so = sd.strideI;
       const long long step = (long long)NBL * so;
       const bool unit = sd.strideB == 1;
@@ -399,18 +470,19 @@ ACC_HD void strided_c2c_pair_body(const StageDesc& d, Ctx& ctx) {
           for (int r = 0; r < RL; ++r) {
             const cplx<T> y = v[u * RL + r];
             if (unit) {
-              store_pair(p + r * step, y, v0, v1);
+              store_pair<Ctx>(d, p + r * step, y, v0, v1);
             } else {
-              if (v0) st_stream(p + r * step, cplx<float>{y.x.a, y.y.a});
-              if (v1) st_stream(p + r * step + sd.strideB, cplx<float>{y.x.b, y.y.b});
+              if (v0) st_g<Ctx>(d, p + r * step, cplx<float>{y.x.a, y.y.a});
+              if (v1) st_g<Ctx>(d, p + r * step + sd.strideB, cplx<float>{y.x.b, y.y.b});
             }
           }
         }
       }
     } else {
+      const int ao = ring_out<Ctx>(d, a);
       pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) {
-        if (v0) store_generic(d, col0, cplx<float>{r.x.a, r.y.a}, k, a, b0);
-        if (v1) store_generic(d, col1, cplx<float>{r.x.b, r.y.b}, k, a, b0 + 1);
+        if (v0) store_generic(d, col0, cplx<float>{r.x.a, r.y.a}, k, ao, b0);
+        if (v1) store_generic(d, col1, cplx<float>{r.x.b, r.y.b}, k, ao, b0 + 1);
       });
     }
   }
@@ -484,8 +556,8 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
   if (valid) {
-    const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB;
-    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = cswap_if(ld_stream(in + i), inv); });
+    const cplx<T>* in = (const cplx<T>*)d.in + (long long)ring_in<Ctx>(d, a) * d.inStrideA + (long long)b * d.inStrideB;
+    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = cswap_if(ld_g<Ctx>(d, in + i), inv); });
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   cplx<T>* stage = (cplx<T>*)ctx.smem() + ((PC * S::SMEM_ELEMS + 1) & ~1);   // only touched when d.staged
@@ -493,9 +565,9 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
   if constexpr (!GEN) {
     if (valid) {
       const SegDst& sd = d.seg[0];
-      cplx<T>* out = (cplx<T>*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB;
+      cplx<T>* out = (cplx<T>*)sd.base + (long long)ring_out<Ctx>(d, a) * sd.strideA + (long long)b * sd.strideB;
       const long long so = sd.strideI;
-      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { st_stream(out + (long long)k * so, cswap_if(r, inv)); });
+      pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { st_g<Ctx>(d, out + (long long)k * so, cswap_if(r, inv)); });
     }
   } else {
     if (valid) {
@@ -536,7 +608,7 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
   if (valid) {
     const cplx<T>* in = (const cplx<T>*)((const T*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB);
-    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = ld_stream(in + i); });
+    pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = ld_g<Ctx>(d, in + i); });
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
@@ -548,13 +620,13 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   if (valid) {
     constexpr int RL = S::radix(S::NP - 1), NBL = S::nb(S::NP - 1), CNTL = S::cnt(S::NP - 1);
     const SegDst& s0 = d.seg[0];
-    cplx<T>* out0 = (cplx<T>*)s0.base + (long long)a * s0.strideA + (long long)b * s0.strideB;
+    cplx<T>* out0 = (cplx<T>*)s0.base + (long long)ring_out<Ctx>(d, a) * s0.strideA + (long long)b * s0.strideB;
     const long long so = s0.strideI;
     OpCol col = {0.0, 0.0, 0};
     if constexpr (GEN) col = op_prepare_if(d, a, b);
     auto put = [&](int kk, cplx<T> y) {
       if constexpr (!GEN) {
-        st_stream(out0 + (long long)kk * so, y);
+        st_g<Ctx>(d, out0 + (long long)kk * so, y);
       } else {
         if (d.staged) stage[staged_index<PC>(d, M + 1, pcl, kk)] = y;
         else store_generic(d, col, y, kk, a, b);
@@ -620,11 +692,11 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
     ACC_UNROLL
     for (int q = 0; q < NLD; ++q) x[q] = {T(0), T(0)};
     if (valid) {
-      const cplx<T>* in = (const cplx<T>*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB;
+      const cplx<T>* in = (const cplx<T>*)d.in + (long long)ring_in<Ctx>(d, a) * d.inStrideA + (long long)b * d.inStrideB;
       ACC_UNROLL
       for (int q = 0; q < NLD; ++q) {
         const int i = t + q * S::G;
-        if (i <= M) x[q] = ld_stream(in + i);
+        if (i <= M) x[q] = ld_g<Ctx>(d, in + i);
       }
       if constexpr (GEN) {
         if (d.op != OP_NONE) {
@@ -684,7 +756,7 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
         out[nidx] = {o.x + r.y, o.y + r.x};
       });
     } else {
-      pass_foreach<S, S::NP - 1>(v, t, [&](int nidx, cplx<T>& r) { st_stream(out + nidx, cswap(r)); });
+      pass_foreach<S, S::NP - 1>(v, t, [&](int nidx, cplx<T>& r) { st_g<Ctx>(d, out + nidx, cswap(r)); });
     }
   }
 }

@@ -133,6 +133,15 @@ int accfftb_plan_profile_read(accfftb_plan* plan, double ms[ACCFFTB_PROFILE_SLOT
  * data (the reference's tuner, src/transpose_gpu.cpp:632-743, runs on the caller's buffers) -- and keep the faster. */
 int accfftb_plan_stage_variant(const accfftb_plan* plan, int slot);
 
+/* The fused local pair.  On a 1 x 1 or slab (P1 == 1) grid the Z and Y passes of a transform are both local to the rank
+ * (the reference's cufftExecD2Z + per-slab cufftExecZ2Z pair, src/accfft_gpu.cpp:477-516, and its mirror :560-602).  For the
+ * length pairs it is compiled for (csrc/fused_combos.def) they run as ONE persistent kernel whose intermediate array is a ring
+ * of a few planes that stays in L2 and never reaches HBM; the launch is profiled in the slot of its first pass (0 forward,
+ * 4 inverse).  dir: 0 forward, 1 inverse.  info (may be NULL) receives what the last such launch used:
+ * {planes per chunk, lag, ring slots, chunks, ring planes (0 = whole buffer), grid, threads, shared memory bytes}.
+ * Returns 1 if the last transform in that direction ran fused, 0 if not (ACCFFT_B200_FUSED=0 switches it off). */
+int accfftb_plan_fused_info(const accfftb_plan* plan, int dir, int info[8]);
+
 long long accfftb_plan_alloc_max(const accfftb_plan* plan);
 /* number of kernels the plan has launched so far (stage kernels + inter-GPU barrier kernels) */
 long long accfftb_plan_launch_count(const accfftb_plan* plan);

@@ -636,7 +636,10 @@ def test_timer_accumulates_and_launch_count(cuda_device):
     back = torch.zeros_like(x)
     p.execute_c2r(out, back)
     prof = p.profile_read()
-    assert all(prof[k][1] == 1 and prof[k][0] > 0 for k in ("fwd_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "inv_z"))
+    # the local Z / Y pair runs as one fused kernel at this size: it is profiled in the slot of its first pass
+    assert p.fused_info(False) is not None and p.fused_info(True) is not None
+    assert all(prof[k][1] == 1 and prof[k][0] > 0 for k in ("fwd_z", "fwd_x", "inv_x", "inv_y"))
+    assert prof["fwd_y"][1] == 0 and prof["inv_z"][1] == 0
     assert prof["barrier"][1] == 0
     p.destroy()
 
@@ -888,3 +891,122 @@ def test_double_buffered_exchange_mixed_operations(cuda_device, monkeypatch, n, 
     assert all(a <= b for a, b in zip(outs_by_mode["db"][1], outs_by_mode["single"][1]))
     if dims[1] == 1 or dims[0] == 1:
         assert outs_by_mode["db"][1][0] < outs_by_mode["single"][1][0]
+
+
+# ---- fused local Z / Y pair (csrc/fused.cuh): one persistent kernel, intermediate planes in an L2-resident ring ----------
+FUSED_CASES = [((64, 64, 64), True, False), ((64, 64, 64), True, True), ((40, 128, 128), True, False), ((24, 256, 256), True, True),
+               ((37, 64, 64), True, False), ((64, 64, 64), False, False), ((20, 128, 128), False, True), ((3, 512, 512), True, False)]
+
+
+@pytest.mark.parametrize("ring", ["auto", "tiny"])
+@pytest.mark.parametrize("n,r2c,single", FUSED_CASES)
+def test_fused_local_pair_matches_separate_kernels(cuda_device, monkeypatch, n, r2c, single, ring):
+    """The fused kernel runs the same tile bodies as the stand-alone Z and Y kernels, so its results must be BITWISE those of
+    the two-kernel path -- with the ring spanning the whole buffer ("auto" at these sizes) and with a ring of two planes and the
+    second pass one chunk behind the first ("tiny": every tile waits on its dependencies, slots are overwritten constantly)."""
+    torch = torch_mod()
+    rdt, cdt = dtypes(single)
+    x = orc.synthetic_real(n, 77) if r2c else orc.synthetic_complex(n, 77)
+    X = orc.forward_r2c(x) if r2c else orc.forward_c2c(x)
+    res = {}
+    for mode in ("fused", "separate"):
+        monkeypatch.setenv("ACCFFT_B200_FUSED", "1" if mode == "fused" else "0")
+        if mode == "fused" and ring == "tiny":
+            for k, v in (("CP", "1"), ("LAG", "1"), ("NS", "2")):
+                monkeypatch.setenv("ACCFFT_B200_FUSED_" + k, v)
+        p = make_plan(n, r2c, single, flags=acc.ACCFFT_ESTIMATE)
+        xd = to_dev(x.astype(rdt if r2c else cdt), cuda_device)
+        xin = xd if r2c else torch.view_as_real(xd).contiguous()
+        out = alloc_out(p, single, cuda_device)
+        back = torch.zeros_like(xin)
+        for _ in range(3):
+            if r2c:
+                p.execute_r2c(xin, out)
+                p.execute_c2r(out, back)
+            else:
+                p.execute_c2c(acc.ACCFFT_FORWARD, xin, out)
+                p.execute_c2c(acc.ACCFFT_BACKWARD, out, back)
+        fi, ii = p.fused_info(False), p.fused_info(True)
+        if mode == "fused":
+            assert fi is not None and ii is not None, "no fused kernel ran for a length pair of fused_combos.def"
+            if ring == "tiny" and n[0] > 2:
+                assert fi["ring_planes"] == 2 and ii["ring_planes"] == 2 and fi["lag"] == 1
+        else:
+            assert fi is None and ii is None
+        res[mode] = (out.cpu().numpy().copy(), back.cpu().numpy().copy())
+        assert orc.rel_l2(spectrum(out, n, single, r2c), X) <= TOL[single]
+        b = back.cpu().numpy()
+        b = b.view(cdt).reshape(n) if not r2c else b
+        assert orc.rel_l2(b, x * x.size) <= TOL[single]
+        # operators ride on the same pair (laplace: forward pair + symbol on X + inverse pair)
+        if r2c:
+            lap = torch.zeros_like(xin)
+            p.laplace(lap, xin)
+            res[mode] += (lap.cpu().numpy().copy(),)
+            assert orc.rel_l2(lap.cpu().numpy(), orc.laplace(x)) <= (1e-11 if not single else 2e-4)
+        p.destroy()
+        for k in ("CP", "LAG", "NS"):
+            monkeypatch.delenv("ACCFFT_B200_FUSED_" + k, raising=False)
+    for a, b in zip(res["fused"], res["separate"]):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,dims,r2c,single", [((64, 64, 64), (2, 1), True, False), ((64, 64, 64), (4, 1), True, True),
+                                               ((30, 128, 128), (4, 1), True, False), ((64, 64, 64), (2, 1), False, False),
+                                               ((16, 64, 64), (8, 1), True, False)])
+@pytest.mark.parametrize("ring", ["auto", "tiny"])
+def test_fused_local_pair_on_slab_grids_threads(cuda_device, monkeypatch, n, dims, r2c, single, ring):
+    """slab grids: forward = fused Z + peer-storing Y (general strided body), inverse = fused local Y + Z behind the exchange;
+    ranks as host threads on cuda:0, uneven and empty slabs included (30 planes over 4 ranks, 16 over 8)"""
+    torch = torch_mod()
+    nprocs = dims[0] * dims[1]
+    rdt, cdt = dtypes(single)
+    tdt = torch.float32 if single else torch.float64
+    es = 4 if single else 8
+    if ring == "tiny":
+        for k, v in (("CP", "1"), ("LAG", "1"), ("NS", "2")):
+            monkeypatch.setenv("ACCFFT_B200_FUSED_" + k, v)
+    x = orc.synthetic_real(n, 91) if r2c else orc.synthetic_complex(n, 91)
+    X = orc.forward_r2c(x) if r2c else orc.forward_c2c(x)
+    comms = [acc.Comm(r, nprocs, dims) for r in range(nprocs)]
+    plans = [acc.Plan(n, comms[r], r2c=r2c, single=single, wire=False, flags=acc.ACCFFT_ESTIMATE) for r in range(nprocs)]
+    acc.attach_local_peers(plans)
+    streams = [torch.cuda.Stream() for _ in range(nprocs)]
+    ins, outs, backs = [], [], []
+    for r in range(nprocs):
+        loc = orc.local_input(x, n, dims, comms[r].coords).astype(rdt if r2c else cdt)
+        t = to_dev(loc, cuda_device) if loc.size else torch.zeros(2, dtype=tdt, device=cuda_device)
+        ins.append(torch.view_as_real(t).contiguous() if (not r2c and loc.size) else t)
+        outs.append(torch.zeros(max(plans[r].alloc_max // es, 2), dtype=tdt, device=cuda_device))
+        backs.append(torch.zeros_like(ins[-1]))
+        plans[r].set_stream(streams[r].cuda_stream)
+    torch.cuda.synchronize()
+
+    def body(r):
+        with torch.cuda.stream(streams[r]):
+            for _ in range(3):
+                if r2c:
+                    plans[r].execute_r2c(ins[r], outs[r])
+                    plans[r].execute_c2r(outs[r], backs[r])
+                else:
+                    plans[r].execute_c2c(acc.ACCFFT_FORWARD, ins[r], outs[r])
+                    plans[r].execute_c2c(acc.ACCFFT_BACKWARD, outs[r], backs[r])
+
+    run_ranks(nprocs, body)
+    torch.cuda.synchronize()
+    assert plans[0].fused_info(False) is not None and plans[0].fused_info(True) is not None
+    blocks = []
+    for r in range(nprocs):
+        osz = plans[r].osize
+        blocks.append(outs[r].cpu().numpy().view(cdt)[:osz[0] * osz[1] * osz[2]].reshape(osz))
+    assert orc.rel_l2(orc.assemble_output(blocks, n, dims, r2c=r2c), X) <= TOL[single]
+    bl = []
+    for r in range(nprocs):
+        isz = plans[r].isize
+        b = backs[r].cpu().numpy().ravel()
+        b = b.view(cdt) if not r2c else b
+        bl.append(b[:isz[0] * isz[1] * isz[2]].reshape(isz))
+    assert orc.rel_l2(orc.assemble_input(bl, n, dims), x * x.size) <= TOL[single]
+    for p in plans:
+        acc.lib().accfftb_plan_destroy(p._h)
+        p._h = None
