@@ -75,6 +75,13 @@ def lib():
     L.accfftb_plan_profile_read.argtypes = [c_vp, c_dp, ctypes.POINTER(c_ll)]
     L.accfftb_plan_stage_variant.argtypes = [c_vp, c_int]
     L.accfftb_plan_fused_info.argtypes = [c_vp, c_int, ip]
+    L.accfftb_plan_create_many.restype = c_vp
+    L.accfftb_plan_create_many.argtypes = [ip, ip, c_int, c_int, c_int, ctypes.c_uint, c_int]
+    L.accfftb_plan_howmany.argtypes = [c_vp]
+    vpp = ctypes.POINTER(c_vp)
+    L.accfftb_execute_r2c_many.argtypes = [c_vp, c_int, vpp, vpp, c_dp]
+    L.accfftb_execute_c2r_many.argtypes = [c_vp, c_int, vpp, vpp, c_dp]
+    L.accfftb_execute_c2c_many.argtypes = [c_vp, c_int, c_int, vpp, vpp, c_dp]
     L.accfftb_plan_alloc_max.restype = c_ll
     L.accfftb_plan_alloc_max.argtypes = [c_vp]
     L.accfftb_plan_launch_count.restype = c_ll
@@ -222,12 +229,15 @@ class Plan:
     (include/accfft_gpu.h:103): plan creation times the two strided-stage kernels on plan-owned scratch and keeps the
     faster one per stage; ACCFFT_ESTIMATE skips the timing and uses a size heuristic."""
 
-    def __init__(self, n, comm: Comm, r2c: bool, single: bool, flags: int = ACCFFT_MEASURE, wire: bool = True):
+    def __init__(self, n, comm: Comm, r2c: bool, single: bool, flags: int = ACCFFT_MEASURE, wire: bool = True, howmany: int = 1):
+        """howmany > 1: a batched plan (accfftb_plan_create_many) -- howmany sets of exchange buffers, execute_*_many take up
+        to howmany fields per call and share the inter-GPU barriers between them"""
         self.n, self.comm, self.r2c, self.single = tuple(int(x) for x in n), comm, r2c, single
+        self.howmany = int(howmany)
         self._local_group = None
         L = lib()
-        self._h = L.accfftb_plan_create(_i3(n), _i2(comm.c_dims), comm.rank, _R2C if r2c else _C2C,
-                                        _FLOAT if single else _DOUBLE, flags)
+        self._h = L.accfftb_plan_create_many(_i3(n), _i2(comm.c_dims), comm.rank, _R2C if r2c else _C2C,
+                                             _FLOAT if single else _DOUBLE, flags, self.howmany)
         err = None if self._h else "plan creation failed: " + _err()
         # plan creation is collective: agree on the outcome before anybody waits for anybody's IPC blob (the C++ layer does
         # the same with an MPI_Allreduce(MIN), csrc/accfft_gpu_api.cpp), so that a failure on one rank raises on ALL ranks
@@ -347,6 +357,33 @@ class Plan:
 
     # ---- single-axis real transforms (accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t, src/accfft_gpu.cpp:1212-1604) -------
     AXES = {"x": 0, "y": 1, "z": 2}
+
+    # ---- batched fields (accfftb_execute_*_many) -------------------------------------------------
+    @staticmethod
+    def _ptr_array(ts):
+        arr = (ctypes.c_void_p * len(ts))()
+        for i, t in enumerate(ts):
+            arr[i] = _ptr(t)
+        return arr
+
+    def execute_r2c_many(self, datas, data_outs, timer=None):
+        """howmany = len(datas) real fields -> their spectra, through one set of exchanges"""
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_execute_r2c_many(self._h, len(datas), self._ptr_array(datas), self._ptr_array(data_outs), p),
+               "accfftb_execute_r2c_many")
+        self._timer_back(arr, timer)
+
+    def execute_c2r_many(self, datas, data_outs, timer=None):
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_execute_c2r_many(self._h, len(datas), self._ptr_array(datas), self._ptr_array(data_outs), p),
+               "accfftb_execute_c2r_many")
+        self._timer_back(arr, timer)
+
+    def execute_c2c_many(self, direction: int, datas, data_outs, timer=None):
+        arr, p = self._timer(timer)
+        _check(lib().accfftb_execute_c2c_many(self._h, direction, len(datas), self._ptr_array(datas), self._ptr_array(data_outs), p),
+               "accfftb_execute_c2c_many")
+        self._timer_back(arr, timer)
 
     def axis_size(self, axis):
         """-> (size, start) of this rank's block of the single-axis half spectrum (osize_xi / osize_yi / osize_0)"""

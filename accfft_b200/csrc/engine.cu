@@ -298,9 +298,10 @@ struct Engine {
   bool l2_persist = false;     // ACCFFT_B200_L2_PERSIST=1: give the hand-off buffer an L2-persisting access-policy window
   size_t l2_window_max = 0;
   long long l2_budget = 0;     // ACCFFT_B200_L2_MB: bytes of intermediate planes kept L2-resident between two local passes (0: off)
-  // fused local Z / Y pair (fused.cuh): ACCFFT_B200_FUSED=0 switches it off; _CP / _LAG / _NS / _HINTS tune it
-  int fused_mode = 1;
-  FusedTune fused_tune = {0, 0, 0, 1};
+  // fused local Z / Y pair (fused.cuh): ACCFFT_B200_FUSED=1 switches it on; _CP / _LAG / _NS tune it (_FLAGS: debugging).
+  // Off by default: measured slower than the two stand-alone kernels although it halves their HBM traffic.
+  int fused_mode = 0;
+  FusedTune fused_tune = {0, 0, 0, 0};
   FusedInfo fused_info[2] = {};   // what the last forward / inverse fused launch used (accfftb_plan_fused_info)
   int* fused_ctr = nullptr;
   static constexpr int kFusedCtrInts = 16384;
@@ -318,6 +319,7 @@ struct Engine {
   char* slab = nullptr;        // [A | B | (A' | B' with double buffering) | flags] of this rank
   size_t slab_bytes = 0, bufsz = 0;
   int nbuf = 2;                // 4 = double buffered exchange buffers (multi-rank plans; ACCFFT_B200_DB=0: 2)
+  int howmany = 1;             // field sets (accfftb_plan_create_many): slab = howmany x [A | B | (A' | B')] | flags
   void* spec = nullptr;        // lazily allocated spectrum scratch for grad / divergence
   int* status_d = nullptr;     // barrier timeout word
   std::vector<void*> opened;   // cudaIpcOpenMemHandle mappings to close
@@ -723,7 +725,7 @@ static void wire_self(Engine* e) {
     e->plan.peerA_alt[e->rank] = e->slab + 2 * e->bufsz;
     e->plan.peerB_alt[e->rank] = e->slab + 3 * e->bufsz;
   }
-  e->flag_ptrs[e->rank] = (unsigned long long*)(e->slab + (size_t)e->nbuf * e->bufsz);
+  e->flag_ptrs[e->rank] = (unsigned long long*)(e->slab + (size_t)e->howmany * e->nbuf * e->bufsz);
 }
 
 // size of rank q's exchange buffers (256-byte aligned) -- every rank can compute it for every peer
@@ -897,6 +899,14 @@ int accfftb_length_supported(int n) { return (length_supported(n) || (n >= 1 && 
 int accfftb_length_fast(int n) { return length_supported(n) ? 1 : 0; }
 
 accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank, int kind, int prec, unsigned flags) {
+  return accfftb_plan_create_many(n, c_dims, rank, kind, prec, flags, 1);
+}
+
+accfftb_plan* accfftb_plan_create_many(const int n[3], const int c_dims[2], int rank, int kind, int prec, unsigned flags, int howmany) {
+  if (howmany < 1 || howmany > 64) {
+    fail(ACCFFTB_ERR_ARG, "accfftb_plan_create_many: howmany must be 1..64");
+    return nullptr;
+  }
   if (!n || !c_dims || n[0] <= 0 || n[1] <= 0 || n[2] <= 0 || c_dims[0] <= 0 || c_dims[1] <= 0 || rank < 0 ||
       rank >= c_dims[0] * c_dims[1] || (kind != ACCFFTB_R2C && kind != ACCFFTB_C2C) ||
       (prec != ACCFFTB_DOUBLE && prec != ACCFFTB_FLOAT)) {
@@ -914,6 +924,8 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
   pl.inplace = false;
   pl.be = &e->be;
   pl.nprocs = c_dims[0] * c_dims[1];
+  e->howmany = howmany;
+  pl.batch = howmany;
   if (!pl.check_supported()) {
     fail(ACCFFTB_ERR_UNSUPPORTED, pl.error);
     delete p;
@@ -931,10 +943,10 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
     e->nbuf = pl.nprocs > 1 ? 4 : 2;
     if (const char* m = getenv("ACCFFT_B200_DB"))
       if (m[0] == '0') e->nbuf = 2;
-    e->slab_bytes = (size_t)e->nbuf * e->bufsz + kFlagBytes;
+    e->slab_bytes = (size_t)e->howmany * e->nbuf * e->bufsz + kFlagBytes;
     err = cudaMalloc((void**)&e->slab, e->slab_bytes);
   }
-  if (err == cudaSuccess) err = cudaMemset(e->slab + (size_t)e->nbuf * e->bufsz, 0, kFlagBytes);
+  if (err == cudaSuccess) err = cudaMemset(e->slab + (size_t)e->howmany * e->nbuf * e->bufsz, 0, kFlagBytes);
   // spectrum scratch of the operators: allocated now, never inside a collective call (cudaMalloc synchronises
   // the device, which must not happen while a peer's barrier kernel waits for this rank)
   if (err == cudaSuccess && kind == ACCFFTB_R2C) err = cudaMalloc(&e->spec, e->bufsz);
@@ -953,7 +965,7 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
   if (const char* m = getenv("ACCFFT_B200_FUSED_CP")) e->fused_tune.cp = atoi(m);
   if (const char* m = getenv("ACCFFT_B200_FUSED_LAG")) e->fused_tune.lag = atoi(m);
   if (const char* m = getenv("ACCFFT_B200_FUSED_NS")) e->fused_tune.ns = atoi(m);
-  if (const char* m = getenv("ACCFFT_B200_FUSED_HINTS")) e->fused_tune.hints = atoi(m);
+  if (const char* m = getenv("ACCFFT_B200_FUSED_FLAGS")) e->fused_tune.flags = atoi(m);
   if (err == cudaSuccess && e->fused_mode && c_dims[1] == 1) err = cudaMalloc((void**)&e->fused_ctr, sizeof(int) * Engine::kFusedCtrInts);
   if (err == cudaSuccess) err = cudaEventCreate(&e->ev[0]);
   if (err == cudaSuccess) err = cudaEventCreate(&e->ev[1]);
@@ -965,6 +977,10 @@ accfftb_plan* accfftb_plan_create(const int n[3], const int c_dims[2], int rank,
     return nullptr;
   }
   wire_self(e);
+  if (e->howmany > 1) {
+    pl.field_stride.resize(pl.nprocs);
+    for (int q = 0; q < pl.nprocs; ++q) pl.field_stride[q] = (long long)e->nbuf * (long long)bufsz_of(e, q);
+  }
   e->wired = pl.nprocs == 1;
   {
     // load every kernel now (see Plan::prepare)
@@ -1056,8 +1072,8 @@ int accfftb_plan_ipc_import(accfftb_plan* plan, const void* blobs, int nblobs) {
     if (b.magic != 0xACCFF7B2u || b.rank != q || b.nprocs != nblobs)
       return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: blob " + std::to_string(q) + " is not rank-ordered / valid");
     const size_t bs = bufsz_of(e, q);
-    if (b.slab_bytes != (size_t)e->nbuf * bs + kFlagBytes)
-      return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: peer plan geometry (or its buffering mode) differs");
+    if (b.slab_bytes != (size_t)e->howmany * e->nbuf * bs + kFlagBytes)
+      return fail(ACCFFTB_ERR_ARG, "accfftb_plan_ipc_import: peer plan geometry (or its buffering mode / field count) differs");
     if (q == e->rank) continue;
     void* base = nullptr;
     CU(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
@@ -1068,7 +1084,7 @@ int accfftb_plan_ipc_import(accfftb_plan* plan, const void* blobs, int nblobs) {
       e->plan.peerA_alt[q] = (char*)base + 2 * bs;
       e->plan.peerB_alt[q] = (char*)base + 3 * bs;
     }
-    e->flag_ptrs[q] = (unsigned long long*)((char*)base + (size_t)e->nbuf * bs);
+    e->flag_ptrs[q] = (unsigned long long*)((char*)base + (size_t)e->howmany * e->nbuf * bs);
   }
   e->wired = true;
   return 0;
@@ -1088,14 +1104,14 @@ int accfftb_plan_attach_local_peers(accfftb_plan* plan, accfftb_plan* const* pla
       if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
       else if (err != cudaSuccess) return cuda_fail(err, "cudaDeviceEnablePeerAccess");
     }
-    if (o->nbuf != e->nbuf) return fail(ACCFFTB_ERR_ARG, "plans differ in their buffering mode");
+    if (o->nbuf != e->nbuf || o->howmany != e->howmany) return fail(ACCFFTB_ERR_ARG, "plans differ in their buffering mode / field count");
     e->plan.peerA[q] = o->slab;
     e->plan.peerB[q] = o->slab + o->bufsz;
     if (e->nbuf == 4) {
       e->plan.peerA_alt[q] = o->slab + 2 * o->bufsz;
       e->plan.peerB_alt[q] = o->slab + 3 * o->bufsz;
     }
-    e->flag_ptrs[q] = (unsigned long long*)(o->slab + (size_t)o->nbuf * o->bufsz);
+    e->flag_ptrs[q] = (unsigned long long*)(o->slab + (size_t)o->howmany * o->nbuf * o->bufsz);
   }
   e->wired = true;
   return 0;
@@ -1231,6 +1247,48 @@ int accfftb_execute_c2c(accfftb_plan* plan, int direction, const void* data, voi
   TimerScope ts(e, timer, 5);
   if (direction == ACCFFTB_FORWARD) return engine_finish(e, e->plan.execute_forward(data, data_out, false, xyz));
   return engine_finish(e, e->plan.execute_inverse(data, data_out, false, xyz));
+}
+
+// ---- batched fields ------------------------------------------------------------------------------------------------
+static int many_args(accfftb_plan* plan, int howmany, const void* const* in, void* const* out) {
+  if (howmany < 1 || howmany > plan->e.howmany)
+    return fail(ACCFFTB_ERR_ARG, "howmany exceeds the field count the plan was made for (accfftb_plan_create_many)");
+  if (!in || !out) return fail(ACCFFTB_ERR_ARG, "null pointer array");
+  for (int f = 0; f < howmany; ++f)
+    if (!in[f] || !out[f]) return fail(ACCFFTB_ERR_ARG, "null data pointer");
+  return 0;
+}
+
+int accfftb_plan_howmany(const accfftb_plan* plan) { return plan ? plan->e.howmany : -1; }
+
+int accfftb_execute_r2c_many(accfftb_plan* plan, int howmany, const void* const* data, void* const* data_out, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, true);
+  if (int rc = many_args(plan, howmany, data, data_out)) return rc;
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 5);
+  return engine_finish(e, e->plan.execute_forward_many(howmany, data, data_out, false));
+}
+
+int accfftb_execute_c2r_many(accfftb_plan* plan, int howmany, const void* const* data, void* const* data_out, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, true);
+  if (int rc = many_args(plan, howmany, data, data_out)) return rc;
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 5);
+  return engine_finish(e, e->plan.execute_inverse_many(howmany, data, data_out, false));
+}
+
+int accfftb_execute_c2c_many(accfftb_plan* plan, int direction, int howmany, const void* const* data, void* const* data_out, double* timer) {
+  const int xyz = 7;
+  CHECK_PLAN(plan, false);
+  if (int rc = many_args(plan, howmany, data, data_out)) return rc;
+  if (direction != ACCFFTB_FORWARD && direction != ACCFFTB_BACKWARD)
+    return fail(ACCFFTB_ERR_ARG, "direction must be ACCFFTB_FORWARD or ACCFFTB_BACKWARD");
+  Engine* e = &plan->e;
+  TimerScope ts(e, timer, 5);
+  if (direction == ACCFFTB_FORWARD) return engine_finish(e, e->plan.execute_forward_many(howmany, data, data_out, false));
+  return engine_finish(e, e->plan.execute_inverse_many(howmany, data, data_out, false));
 }
 
 static int ensure_spec(Engine* e) {

@@ -17,6 +17,7 @@
 // addressing; ring data is read with ld.global.cg (L2), everything else streams (evict-first).
 #pragma once
 #include <cuda_runtime.h>
+#include "cuda_ctx.cuh"
 #include "kernel_cfg.hpp"
 #include "launch.hpp"
 
@@ -29,12 +30,132 @@ struct FusedArgs {
   int t1, t2;        // tiles per chunk of pass 1 / pass 2
   int tpa;           // strided pass: tiles per plane
   int tz;            // contiguous pass: tiles per chunk (= cp * pencils per plane / PCZ)
+  int zfirst;        // 1: pass 1 is the contiguous (Z) pass (forward), 0: the strided one (inverse)
+  int ztiles, yplanes;   // tiles of the contiguous pass / planes of the strided pass that exist (the last chunk may be ragged)
+  int flags;         // debugging: bit 0 = signal a tile's completion right away (not from the next tile's hook),
+                     //            bit 1 = no early dependency check (every tile polls)
+                     //            bit 2 = TIMING EXPERIMENT, results invalid: no dependency waits, no signals
+                     //            bit 3 = static work assignment (item = CTA + k * grid) instead of the global counter
   long long total;   // work items = (nch + lag) * (t1 + t2)
 };
 
+__device__ __forceinline__ int fused_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int fused_ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// what the scheduler publishes for a work item
+enum FusedKind : int { FK_END = 0, FK_DEAD = 1, FK_EMPTY = 2, FK_Z = 3, FK_Y = 4 };
+struct FusedSlot {
+  int kind;    // FK_END: list exhausted; FK_DEAD: chunk out of range, nothing to do; FK_EMPTY: a tile beyond the ragged end (signals
+               // only); FK_Z / FK_Y: run the contiguous / strided body on tile `bid`
+  int ready;   // its dependency was found satisfied by the early check
+  int bid;     // tile index in the body's own numbering
+  int sig;     // index into ctr of the counter the tile increments when done
+  int dep;     // index into ctr of the counter it waits for (0: none) ...
+  int target;  // ... and the value that counter must reach
+};
+
+// scheduler state of a CTA (shared memory; only thread 0 touches anything but `next`)
+struct FusedSched {
+  FusedArgs fa;
+  int pending;     // ctr index of the previous tile's completion counter, not yet signalled (0: none)
+  int slot;        // slot of `next` the next item is published to
+  int hooked;      // the scheduler has run for the current tile
+  FusedSlot next[2];
+};
+__device__ __forceinline__ FusedSched& fused_sched() {
+  __shared__ FusedSched ss;
+  return ss;
+}
+
+__device__ __forceinline__ FusedSlot fused_decode(const FusedArgs& fa, int w) {
+  FusedSlot it;
+  it.ready = 0, it.bid = 0, it.sig = 0, it.dep = 0, it.target = 0;
+  if ((long long)w >= fa.total) {
+    it.kind = FK_END;
+    return it;
+  }
+  const int per = fa.t1 + fa.t2;
+  const int s = w / per, i = w - s * per;
+  const bool ph1 = i < fa.t1;
+  const int c = ph1 ? s : s - fa.lag;
+  const int t = ph1 ? i : i - fa.t1;
+  if (c < 0 || c >= fa.nch) {
+    it.kind = FK_DEAD;
+    return it;
+  }
+  if (ph1) {
+    it.sig = 1 + c;
+    if (c >= fa.ns) it.dep = 1 + fa.nch + (c - fa.ns), it.target = fa.t2;
+  } else {
+    it.sig = 1 + fa.nch + c;
+    it.dep = 1 + c, it.target = fa.t1;
+  }
+  const bool ztype = ph1 == (fa.zfirst != 0);
+  if (ztype) {
+    it.bid = c * fa.tz + t;
+    it.kind = it.bid < fa.ztiles ? FK_Z : FK_EMPTY;
+  } else {
+    it.bid = c * fa.cp * fa.tpa + t;
+    it.kind = it.bid / fa.tpa < fa.yplanes ? FK_Y : FK_EMPTY;
+  }
+  return it;
+}
+
+// Execution context of a tile inside the fused kernel.  Besides the ring addressing (RIN / ROUT: the stage's input / output is
+// the ring) it carries the tile scheduler, which runs in thread 0 from the `after_loads` hook the stage bodies call once their
+// global loads are issued -- i.e. in the shadow of the tile's own memory latency instead of between two tiles:
+//   * the completion signal of the PREVIOUS tile (fence + counter increment) is sent there,
+//   * the NEXT work item (claimed from the global counter when this tile started) is decoded, its dependency counter is read
+//     once, and the decoded item + "dependency already satisfied" are published to shared memory for the next loop iteration.
+// The loop itself then costs one CTA barrier per tile; it polls only when that early check failed (after flushing the pending
+// signal, so that a CTA never waits while it holds back a signal).
+struct FusedSchedOps {
+  static __device__ __forceinline__ void flush() {
+    FusedSched& ss = fused_sched();
+    if (ss.pending) {
+      __threadfence();
+      atomicAdd(ss.fa.ctr + ss.pending, 1);
+      ss.pending = 0;
+    }
+  }
+  static __device__ __noinline__ void sched(int claim) {
+    FusedSched& ss = fused_sched();
+    ss.hooked = 1;
+    FusedSlot it = fused_decode(ss.fa, claim);
+    if (ss.fa.flags & 4) {   // timing experiment: no synchronisation at all
+      it.ready = 1;
+      it.sig = 0;
+      ss.next[ss.slot] = it;
+      return;
+    }
+    int depv = 0;
+    if (it.dep && !(ss.fa.flags & 2)) depv = fused_ld_relaxed(ss.fa.ctr + it.dep);
+    __threadfence();   // releases this CTA's earlier stores for the signal below AND makes the relaxed load above an acquire
+    if (ss.pending) {
+      atomicAdd(ss.fa.ctr + ss.pending, 1);
+      ss.pending = 0;
+    }
+    it.ready = (it.dep == 0 || (depv >= it.target && !(ss.fa.flags & 2))) ? 1 : 0;
+    ss.next[ss.slot] = it;
+  }
+};
+
+template <bool RIN, bool ROUT>
 struct FusedCtx {
   static constexpr bool kRing = true;
+  static constexpr bool kRingIn = RIN;
+  static constexpr bool kRingOut = ROUT;
+  static constexpr bool kGroupSync = true;
   long long bid_;
+  int claim;      // thread 0: the next work item (in flight from the global counter while the tile loads)
   __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
   __device__ __forceinline__ long long bid() const { return bid_; }
   __device__ __forceinline__ void* smem() const {
@@ -42,9 +163,16 @@ struct FusedCtx {
     return accfft_smem_raw;
   }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
+  template <int G, int PC>
+  __device__ __forceinline__ void sync_group(int pcl) const {
+    cuda_sync_group<G, PC>(pcl);
+  }
   __device__ __forceinline__ void bulk_fence() const {}
   __device__ __forceinline__ void bulk_store(void*, const void*, unsigned) const {}
   __device__ __forceinline__ void bulk_wait() const {}
+  __device__ __forceinline__ void after_loads() const {
+    if (threadIdx.x == 0 && !fused_sched().hooked) FusedSchedOps::sched(claim);
+  }
 };
 
 // CTA shape: the strided pass decides the thread count (its tile = 128-byte row segments), the contiguous pass takes
@@ -63,14 +191,10 @@ struct FusedCfg {
     return m;
   }
   static constexpr int MINB = minb();
-  static constexpr bool OK = PCZ >= 1 && THREADS % SZ::G == 0 && THREADS <= 1024 && SMEM <= 220 * 1024;
+  // (shapes that leave an SM with fewer than 768 resident threads lose more in the contiguous pass than the ring saves:
+  // measured 25 ms vs 13 ms at 1024^3 single, whose strided tile holds 16 lane pairs per thread at one CTA per SM)
+  static constexpr bool OK = PCZ >= 1 && THREADS % SZ::G == 0 && THREADS <= 1024 && SMEM <= 220 * 1024 && THREADS * MINB >= 768;
 };
-
-__device__ __forceinline__ int fused_ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // MODE 0: forward r2c (contig r2c -> strided), 1: inverse c2r (strided -> contig c2r),
 //      2: forward c2c (contig c2c -> strided), 3: inverse c2c (strided -> contig c2c).  GENY: the strided pass is the general
@@ -80,54 +204,63 @@ __global__ void __launch_bounds__(FusedCfg<T, SZ, SY>::THREADS, FusedCfg<T, SZ, 
     k_fused(const __grid_constant__ StageDesc dz, const __grid_constant__ StageDesc dy, const FusedArgs fa) {
   using C = FusedCfg<T, SZ, SY>;
   constexpr bool Z_FIRST = (MODE == 0 || MODE == 2);
-  __shared__ int s_item;
+  // the ring is the output of the first pass and the input of the second
+  using CtxZ = FusedCtx<!Z_FIRST, Z_FIRST>;
+  using CtxY = FusedCtx<Z_FIRST, !Z_FIRST>;
+  FusedSched& ss = fused_sched();
   const int tid = (int)threadIdx.x;
-  int* const done1 = fa.ctr + 1;
-  int* const done2 = fa.ctr + 1 + fa.nch;
-  const int per = fa.t1 + fa.t2;
+  int claim = 0;
+  if (tid == 0) {
+    ss.fa = fa;
+    ss.pending = 0;
+    ss.slot = 0;
+    ss.hooked = 0;
+    FusedSchedOps::sched((fa.flags & 8) ? (int)blockIdx.x : atomicAdd(fa.ctr, 1));   // publishes the first item to slot 0
+  }
+  __syncthreads();
 #pragma unroll 1
-  for (;;) {
-    if (tid == 0) s_item = atomicAdd(fa.ctr, 1);
-    __syncthreads();
-    const long long w = s_item;
-    if (w >= fa.total) break;
-    const int s = (int)(w / per), i = (int)(w % per);
-    const bool ph1 = i < fa.t1;
-    const int c = ph1 ? s : s - fa.lag;
-    const int t = ph1 ? i : i - fa.t1;
-    const bool live = c >= 0 && c < fa.nch;
-    if (live && tid == 0) {
-      if (ph1) {
-        if (c >= fa.ns)
-          while (fused_ld_acquire(done2 + c - fa.ns) < fa.t2) __nanosleep(64);
-      } else {
-        while (fused_ld_acquire(done1 + c) < fa.t1) __nanosleep(64);
+  for (int iter = 0;; ++iter) {
+    const int slot = iter & 1;
+    const int kind = ss.next[slot].kind;
+    const int bid = ss.next[slot].bid;
+    if (kind == FK_END) break;
+    if (kind != FK_DEAD && !ss.next[slot].ready) {   // rare: the early check in sched() found the dependency open
+      if (tid == 0) {
+        FusedSchedOps::flush();
+        const int* dep = fa.ctr + ss.next[slot].dep;
+        const int target = ss.next[slot].target;
+        while (fused_ld_acquire(dep) < target) __nanosleep(64);
       }
+      __syncthreads();
     }
-    __syncthreads();   // (also: everyone has read s_item before thread 0 claims the next item)
-    if (!live) continue;
-    const bool ztype = ph1 == Z_FIRST;
-    FusedCtx ctx;
-    if (ztype) {
-      ctx.bid_ = (long long)c * fa.tz + t;
-      if (ctx.bid_ * C::PCZ < (long long)dz.nA * dz.nB) {
-        if constexpr (MODE == 0) contig_r2c_body<T, SZ, C::PCZ, false>(dz, ctx);
-        else if constexpr (MODE == 1) contig_c2r_body<T, SZ, C::PCZ, false>(dz, ctx);
-        else contig_c2c_body<T, SZ, C::PCZ, false>(dz, ctx);
-      }
-    } else {
-      ctx.bid_ = (long long)c * fa.cp * fa.tpa + t;
-      if (ctx.bid_ / fa.tpa < dy.nA) {
-        if constexpr (C::F) strided_c2c_pair_body<SY, PairCfg<SY>::TCP, GENY>(dy, ctx);
-        else strided_c2c_body<T, SY, Cfg<T, SY>::TC, GENY>(dy, ctx);
-      }
-    }
-    __syncthreads();   // every thread's stores are issued (and the tile's shared memory is free)
     if (tid == 0) {
-      __threadfence();
-      atomicAdd(ph1 ? done1 + c : done2 + c, 1);
+      claim = (fa.flags & 8) ? (int)blockIdx.x + (iter + 1) * (int)gridDim.x
+                             : atomicAdd(fa.ctr, 1);   // consumed in sched(), a memory latency from now
+      ss.slot = slot ^ 1;
+      ss.hooked = 0;
+    }
+    if (kind == FK_Z) {
+      CtxZ ctx;
+      ctx.bid_ = bid;
+      ctx.claim = claim;
+      if constexpr (MODE == 0) contig_r2c_body<T, SZ, C::PCZ, false>(dz, ctx);
+      else if constexpr (MODE == 1) contig_c2r_body<T, SZ, C::PCZ, false>(dz, ctx);
+      else contig_c2c_body<T, SZ, C::PCZ, false>(dz, ctx);
+    } else if (kind == FK_Y) {
+      CtxY ctx;
+      ctx.bid_ = bid;
+      ctx.claim = claim;
+      if constexpr (C::F) strided_c2c_pair_body<SY, PairCfg<SY>::TCP, GENY>(dy, ctx);
+      else strided_c2c_body<T, SY, Cfg<T, SY>::TC, GENY>(dy, ctx);
+    }
+    if (tid == 0 && !ss.hooked) FusedSchedOps::sched(claim);   // (no tile, or thread 0 had nothing to load)
+    __syncthreads();   // every thread's stores are issued, the tile's shared memory is free, the next item is published
+    if (tid == 0 && kind != FK_DEAD && !(fa.flags & 4)) {
+      ss.pending = ss.next[slot].sig;
+      if (fa.flags & 1) FusedSchedOps::flush();
     }
   }
+  if (tid == 0) FusedSchedOps::flush();
 }
 
 }  // namespace accfft_b200

@@ -9,7 +9,7 @@ struct FusedTune {
   int cp;      // planes of the outer index per chunk (0: default)
   int lag;     // chunks the second pass runs behind the first (0: derived from the number of resident CTAs)
   int ns;      // ring slots in chunks (0: lag + 2)
-  int hints;   // 1: evict-first hints on the accesses that do not touch the ring
+  int flags;   // debugging (FusedArgs::flags): 1 = signal tiles right away, 2 = no early dependency check
 };
 struct FusedInfo {
   int cp, lag, ns, nch, ring_planes, grid, threads, smem;

@@ -55,11 +55,11 @@ static int fused_launch_one(const Launch& lz, const Launch& ly, const FusedTune&
     if (geny && !FWD) return -2;
     if (C::F && dy.inStrideB != 1) return -2;
     const int nA = dz.nA;
-    int cp = tune.cp > 0 ? tune.cp : 2;
-    while (cp <= 64 && ((long long)cp * dz.nB) % C::PCZ != 0) ++cp;
+    // planes per chunk: a power of two (the ring is addressed with a mask) whose pencils fill whole contiguous-pass tiles
+    int cp = 1;
+    while (cp < (tune.cp > 0 ? tune.cp : 2)) cp *= 2;
+    while (cp <= 64 && ((long long)cp * dz.nB) % C::PCZ != 0) cp *= 2;
     if (cp > 64) return -2;
-    if (cp > nA) cp = nA;
-    if (((long long)cp * dz.nB) % C::PCZ != 0) return -2;
     constexpr int TCE = C::F ? 2 * PairCfg<SY>::TCP : Cfg<T, SY>::TC;
     FusedArgs fa;
     fa.ctr = ctr;
@@ -75,20 +75,25 @@ static int fused_launch_one(const Launch& lz, const Launch& ly, const FusedTune&
     int lag = tune.lag > 0 ? tune.lag : (int)((3 * grid / 2 + per - 1) / per);
     if (lag < 1) lag = 1;
     int ns = tune.ns > lag ? tune.ns : lag + 2;
+    {   // ring slots: a power of two
+      int p2 = 1;
+      while (p2 < ns) p2 *= 2;
+      ns = p2;
+    }
     fa.lag = lag;
     fa.ns = ns;
+    fa.zfirst = FWD ? 1 : 0;
+    fa.ztiles = (int)(((long long)dz.nA * dz.nB + C::PCZ - 1) / C::PCZ);
+    fa.yplanes = dy.nA;
+    fa.flags = tune.flags;
+    if ((long long)(fa.nch + lag) * per > 0x3fffffffLL) return -2;
     fa.total = (long long)(fa.nch + lag) * per;
     if (1 + 2 * fa.nch > ctr_ints) return -2;
-    const long long ring = (long long)ns * cp;
-    const int ringA = ring >= nA ? 0 : (int)ring;   // a ring as long as the array is plain addressing
-    if (FWD) dz.outRing = ringA, dy.inRing = ringA;
-    else dy.outRing = ringA, dz.inRing = ringA;
-    // without a ring the consumer still reads what other SMs wrote during this kernel: keep the L2-only loads
-    if (!ringA) {
-      if (FWD) dy.inRing = 0x7fffffff;
-      else dz.inRing = 0x7fffffff;
-    }
-    dz.ringHints = dy.ringHints = tune.hints;
+    const long long ring = (long long)ns * cp;          // planes, a power of two
+    const int ringA = ring >= nA ? 0 : (int)ring;       // a ring as long as the array is plain addressing (mask = all ones)
+    const int mask = ringA ? ringA - 1 : 0x7fffffff;
+    if (FWD) dz.outRing = mask, dy.inRing = mask;
+    else dy.outRing = mask, dz.inRing = mask;
     if (info) {
       info->cp = cp, info->lag = lag, info->ns = ns, info->nch = fa.nch, info->ring_planes = ringA, info->grid = (int)grid;
       info->threads = C::THREADS, info->smem = C::SMEM;

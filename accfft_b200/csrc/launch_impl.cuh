@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include "kernel_cfg.hpp"
 #include "launch.hpp"
+#include "cuda_ctx.cuh"
 #if ACCFFT_KIND == 4
 #include "stage_tma.cuh"
 #endif
@@ -20,6 +21,12 @@ struct CudaCtx {
     return accfft_smem_raw;
   }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
+  // barrier among the G threads of pencil `pcl` only (stage.cuh: group_sync)
+  static constexpr bool kGroupSync = true;
+  template <int G, int PC>
+  __device__ __forceinline__ void sync_group(int pcl) const {
+    cuda_sync_group<G, PC>(pcl);
+  }
   // bulk (TMA) copy shared -> global; the destination may be a peer-mapped buffer (NVLink).  16-byte aligned
   // addresses and size.  Generic-proxy writes to the source must be fenced (bulk_fence) and CTA-synchronised first.
   __device__ __forceinline__ void bulk_fence() const { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -732,6 +732,64 @@ int Plan::execute_inverse(const void* in, void* out, bool out_padded, int xyz) {
   return 0;
 }
 
+// ---- batched fields: every stage for all fields, then ONE barrier ----------------------------------------------------
+int Plan::execute_forward_many(int nf, const void* const* in, void* const* out, bool in_padded) {
+  if (nf < 1 || nf > batch) {
+    error = "execute_*_many: the plan was made for fewer fields (accfftb_plan_create_many)";
+    return -3;
+  }
+  if (nf == 1) return execute_forward(in[0], out[0], in_padded);
+  int rc;
+  flip();
+  for (int f = 0; f < nf; ++f) {
+    FieldScope fs(*this, f);
+    Launch z = fwd_z(in[f], in_padded);
+    if (!empty(z) && (rc = be->launch(z))) return rc;
+  }
+  if ((rc = bar_if(row_exchanges()))) return rc;
+  for (int f = 0; f < nf; ++f) {
+    FieldScope fs(*this, f);
+    Launch y = fwd_y();
+    if (!empty(y) && (rc = be->launch(y))) return rc;
+  }
+  if ((rc = bar_if(col_exchanges()))) return rc;
+  for (int f = 0; f < nf; ++f) {
+    FieldScope fs(*this, f);
+    Launch x = fwd_x(out[f]);
+    if (!empty(x) && (rc = be->launch(x))) return rc;
+  }
+  return 0;
+}
+
+int Plan::execute_inverse_many(int nf, const void* const* in, void* const* out, bool out_padded) {
+  if (nf < 1 || nf > batch) {
+    error = "execute_*_many: the plan was made for fewer fields (accfftb_plan_create_many)";
+    return -3;
+  }
+  if (nf == 1) return execute_inverse(in[0], out[0], out_padded);
+  int rc;
+  flip();
+  if ((rc = a_fence())) return rc;
+  for (int f = 0; f < nf; ++f) {
+    FieldScope fs(*this, f);
+    Launch x = inv_x(in[f]);
+    if (!empty(x) && (rc = be->launch(x))) return rc;
+  }
+  if ((rc = bar_if(col_exchanges()))) return rc;
+  for (int f = 0; f < nf; ++f) {
+    FieldScope fs(*this, f);
+    Launch y = inv_y();
+    if (!empty(y) && (rc = be->launch(y))) return rc;
+  }
+  if ((rc = bar_if(row_exchanges()))) return rc;
+  for (int f = 0; f < nf; ++f) {
+    FieldScope fs(*this, f);
+    Launch z = inv_z(out[f], out_padded);
+    if (!empty(z) && (rc = be->launch(z))) return rc;
+  }
+  return 0;
+}
+
 int Plan::execute_spectral(const void* in, void* out, int op, void* spec, double opA, double opB) {
   int rc;
   flip();
@@ -783,6 +841,36 @@ int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spe
   x.desc.op = OP_SCALE;
   x.desc.scale = inv_n;
   if (!empty(x) && (rc = be->launch(x))) return rc;
+  if (batch >= 3 && nprocs > 1) {
+    // vector-field batch: the inverses of the selected components go through ONE set of exchanges (field set `ax` each)
+    flip();
+    for (int ax = 0; ax < 3; ++ax) {
+      if (!(comps & (1 << ax))) continue;
+      FieldScope fs(*this, ax);
+      Launch xi = inv_x(spec);
+      xi.desc.op = OP_GRAD;
+      xi.desc.opAxis = ax;
+      xi.desc.scale = 1.0;
+      xi.desc.opOnLoad = 1;
+      xi.desc.opFullAxis = pair_rule ? 0 : 1;
+      if (!empty(xi) && (rc = be->launch(xi))) return rc;
+    }
+    if ((rc = bar_if(col_exchanges()))) return rc;
+    for (int ax = 0; ax < 3; ++ax) {
+      if (!(comps & (1 << ax))) continue;
+      FieldScope fs(*this, ax);
+      Launch yi = inv_y();
+      if (!empty(yi) && (rc = be->launch(yi))) return rc;
+    }
+    if ((rc = bar_if(row_exchanges()))) return rc;
+    for (int ax = 0; ax < 3; ++ax) {
+      if (!(comps & (1 << ax))) continue;
+      FieldScope fs(*this, ax);
+      Launch zi = inv_z(outs[ax], false);
+      if (!empty(zi) && (rc = be->launch(zi))) return rc;
+    }
+    return 0;
+  }
   for (int ax = 0; ax < 3; ++ax) {
     if (!(comps & (1 << ax))) continue;
     flip();
@@ -806,6 +894,32 @@ int Plan::execute_grad(const void* in, void* const outs[3], int comps, void* spe
 int Plan::execute_divergence(const void* const ins[3], void* out, void* spec, bool pair_rule) {
   int rc;
   const double inv_n = 1.0 / ((double)g.n[0] * (double)g.n[1] * (double)g.n[2]);
+  if (batch >= 3 && nprocs > 1) {
+    // vector-field batch: the three forward transforms share one set of exchanges; the X stages accumulate in stream order
+    flip();
+    for (int ax = 0; ax < 3; ++ax) {
+      FieldScope fs(*this, ax);
+      Launch z = fwd_z(ins[ax], false);
+      if (!empty(z) && (rc = be->launch(z))) return rc;
+    }
+    if ((rc = bar_if(row_exchanges()))) return rc;
+    for (int ax = 0; ax < 3; ++ax) {
+      FieldScope fs(*this, ax);
+      Launch y = fwd_y();
+      if (!empty(y) && (rc = be->launch(y))) return rc;
+    }
+    if ((rc = bar_if(col_exchanges()))) return rc;
+    for (int ax = 0; ax < 3; ++ax) {
+      FieldScope fs(*this, ax);
+      Launch x = fwd_x(spec);
+      x.desc.op = OP_GRAD;
+      x.desc.opAxis = ax;
+      x.desc.scale = inv_n;
+      x.desc.opFullAxis = pair_rule ? 0 : 1;
+      x.desc.accumulate = ax > 0;
+      if (!empty(x) && (rc = be->launch(x))) return rc;
+    }
+  } else
   for (int ax = 0; ax < 3; ++ax) {
     flip();
     Launch z = fwd_z(ins[ax], false);

@@ -101,6 +101,26 @@ struct Plan {
       peerB.swap(peerB_alt);
     }
   }
+  // Batched fields (the reference's howmany > 1 exchange path, src/transpose_gpu.cpp:4454-4726): a plan made for
+  // `batch` fields owns `batch` sets of exchange buffers per rank; field f of rank q lives field_stride[q] * f bytes behind
+  // field 0 in every buffer of that rank.  execute_*_many run every stage for all fields back to back and share the
+  // barriers: one exchange synchronisation per stage for the whole batch instead of one per field.
+  int batch = 1;
+  std::vector<long long> field_stride;   // per rank, bytes (empty: batch == 1)
+  void shift_fields(int f, int sign) {
+    if (f == 0 || field_stride.empty()) return;
+    for (std::vector<void*>* v : {&peerA, &peerB, &peerA_alt, &peerB_alt})
+      for (size_t q = 0; q < v->size(); ++q)
+        if ((*v)[q]) (*v)[q] = (char*)(*v)[q] + (long long)sign * f * field_stride[q];
+  }
+  struct FieldScope {   // stage descriptors built inside the scope address field f's buffers
+    Plan& p;
+    int f;
+    FieldScope(Plan& p_, int f_) : p(p_), f(f_) { p.shift_fields(f, +1); }
+    ~FieldScope() { p.shift_fields(f, -1); }
+  };
+  int execute_forward_many(int nf, const void* const* in, void* const* out, bool in_padded);
+  int execute_inverse_many(int nf, const void* const* in, void* const* out, bool out_padded);
   bool row_exchanges() const { return g.np[1] > 1; }   // Z <-> Y hand-off crosses ranks
   bool col_exchanges() const { return g.np[0] > 1; }   // Y <-> X hand-off crosses ranks
   int bar_if(bool data);   // barrier if it orders data, or (single buffering) buffer reuse

@@ -73,8 +73,7 @@ struct StageDesc {
   // Fused two-pass kernel (fused.cuh): the buffer between the two passes is used as a RING of a few planes of the outer
   // index a (plane a lives at slot a % ring) that stays resident in L2, so the intermediate array never reaches HBM.
   // Only honoured by kernels whose context says so (ctx_ring); 0 = plain addressing.
-  int inRing, outRing;
-  int ringHints;         // 1: accesses that do NOT touch the ring are marked evict-first (they stream through L2 once)
+  int inRing, outRing;   // ring - 1 (ring = a power of two planes); accesses that do NOT touch the ring are marked evict-first
 };
 
 // does this execution context run ring-addressed stages (the fused persistent kernel)?  Default: no.
@@ -83,13 +82,37 @@ struct ctx_ring : std::false_type {};
 template <class Ctx>
 struct ctx_ring<Ctx, std::void_t<decltype(Ctx::kRing)>> : std::integral_constant<bool, Ctx::kRing> {};
 
+// (inRing / outRing hold ring - 1 with ring a power of two, i.e. a mask; which side of a stage is the ring is a compile-time
+// property of the context: Ctx::kRingIn / Ctx::kRingOut)
 template <class Ctx> ACC_HD int ring_in(const StageDesc& d, int a) {
-  if constexpr (ctx_ring<Ctx>::value) return d.inRing ? a % d.inRing : a;
-  else return a;
+  if constexpr (ctx_ring<Ctx>::value) {
+    if constexpr (Ctx::kRingIn) return a & d.inRing;
+    else return a;
+  } else {
+    return a;
+  }
 }
 template <class Ctx> ACC_HD int ring_out(const StageDesc& d, int a) {
-  if constexpr (ctx_ring<Ctx>::value) return d.outRing ? a % d.outRing : a;
-  else return a;
+  if constexpr (ctx_ring<Ctx>::value) {
+    if constexpr (Ctx::kRingOut) return a & d.outRing;
+    else return a;
+  } else {
+    return a;
+  }
+}
+
+// Barrier among the G threads that work on ONE pencil of a contiguous stage (pencil `pcl` of the CTA's PC): the pencils of a
+// CTA share nothing, so a CTA-wide barrier only makes every pencil wait for the slowest one.  Contexts that can do better
+// (Ctx::kGroupSync: warp-level sync when a pencil's threads sit inside one warp, a named barrier per pencil when they are whole
+// warps) provide sync_group; everything else (the CPU emulator) falls back to the CTA barrier, which is always sufficient.
+template <class Ctx, class = void>
+struct ctx_group_sync : std::false_type {};
+template <class Ctx>
+struct ctx_group_sync<Ctx, std::void_t<decltype(Ctx::kGroupSync)>> : std::integral_constant<bool, Ctx::kGroupSync> {};
+template <int G, int PC, class Ctx>
+ACC_HD void group_sync(Ctx& ctx, int pcl) {
+  if constexpr (ctx_group_sync<Ctx>::value) ctx.template sync_group<G, PC>(pcl);
+  else ctx.sync();
 }
 
 // global loads / stores of a stage.  In a ring context, ring data is read with ld.global.cg (L2 only: another SM wrote it
@@ -99,12 +122,10 @@ ACC_HD cplx<T> ld_g(const StageDesc& d, const cplx<T>* p) {
 #if defined(__CUDA_ARCH__)
   if constexpr (ctx_ring<Ctx>::value) {
     if constexpr (sizeof(T) == 8) {
-      const double2 v = d.inRing ? __ldcg(reinterpret_cast<const double2*>(p))
-                                 : (d.ringHints ? __ldcs(reinterpret_cast<const double2*>(p)) : *reinterpret_cast<const double2*>(p));
+      const double2 v = Ctx::kRingIn ? __ldcg(reinterpret_cast<const double2*>(p)) : __ldcs(reinterpret_cast<const double2*>(p));
       return {v.x, v.y};
     } else {
-      const float2 v = d.inRing ? __ldcg(reinterpret_cast<const float2*>(p))
-                                : (d.ringHints ? __ldcs(reinterpret_cast<const float2*>(p)) : *reinterpret_cast<const float2*>(p));
+      const float2 v = Ctx::kRingIn ? __ldcg(reinterpret_cast<const float2*>(p)) : __ldcs(reinterpret_cast<const float2*>(p));
       return {v.x, v.y};
     }
   }
@@ -115,7 +136,7 @@ template <class Ctx, class T>
 ACC_HD void st_g(const StageDesc& d, cplx<T>* p, cplx<T> v) {
 #if defined(__CUDA_ARCH__)
   if constexpr (ctx_ring<Ctx>::value) {
-    if (!d.outRing && d.ringHints) {
+    if constexpr (!Ctx::kRingOut) {
       if constexpr (sizeof(T) == 8) __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
       else __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
       return;
@@ -314,6 +335,7 @@ ACC_HD void strided_c2c_body(const StageDesc& d, Ctx& ctx) {
         for (int r = 0; r < R0; ++r) v[u * R0 + r] = ld_g<Ctx>(d, p + r * step);
       }
     }
+    if constexpr (ctx_ring<Ctx>::value) ctx.after_loads();
     if constexpr (GEN) {
       if (d.opOnLoad) pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = apply_op(d, col, r, i); });
     }
@@ -368,8 +390,7 @@ ACC_HD cplx<f2> load_pair(const StageDesc& d, const cplx<float>* p, bool v0, boo
   if (v0 && v1 && (((unsigned long long)p) & 15ull) == 0) {
 #if defined(__CUDA_ARCH__)
     if constexpr (ctx_ring<Ctx>::value) {
-      const float4 q = d.inRing ? __ldcg(reinterpret_cast<const float4*>(p))
-                                : (d.ringHints ? __ldcs(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p));
+      const float4 q = Ctx::kRingIn ? __ldcg(reinterpret_cast<const float4*>(p)) : __ldcs(reinterpret_cast<const float4*>(p));
       return {f2(q.x, q.z), f2(q.y, q.w)};
     }
 #endif
@@ -385,7 +406,7 @@ ACC_HD void store_pair(const StageDesc& d, cplx<float>* p, cplx<f2> v, bool v0, 
   if (v0 && v1 && (((unsigned long long)p) & 15ull) == 0) {
 #if defined(__CUDA_ARCH__)
     if constexpr (ctx_ring<Ctx>::value) {
-      if (!d.outRing && d.ringHints) {
+      if constexpr (!Ctx::kRingOut) {
         __stcs(reinterpret_cast<float4*>(p), make_float4(v.x.a, v.y.a, v.x.b, v.y.b));
         return;
       }
@@ -435,6 +456,7 @@ ACC_HD void strided_c2c_pair_body(const StageDesc& d, Ctx& ctx) {
         for (int r = 0; r < R0; ++r) v[u * R0 + r] = load_pair<Ctx>(d, p + r * step, v0, v1);
       }
     }
+    if constexpr (ctx_ring<Ctx>::value) ctx.after_loads();
     if constexpr (GEN) {
       if (d.opOnLoad)
         pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) {
@@ -558,10 +580,11 @@ ACC_HD void contig_c2c_body(const StageDesc& d, Ctx& ctx) {
   if (valid) {
     const cplx<T>* in = (const cplx<T>*)d.in + (long long)ring_in<Ctx>(d, a) * d.inStrideA + (long long)b * d.inStrideB;
     pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = cswap_if(ld_g<Ctx>(d, in + i), inv); });
+    if constexpr (ctx_ring<Ctx>::value) ctx.after_loads();
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   cplx<T>* stage = (cplx<T>*)ctx.smem() + ((PC * S::SMEM_ELEMS + 1) & ~1);   // only touched when d.staged
-  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { group_sync<S::G, PC>(ctx, pcl); });
   if constexpr (!GEN) {
     if (valid) {
       const SegDst& sd = d.seg[0];
@@ -609,14 +632,15 @@ ACC_HD void contig_r2c_body(const StageDesc& d, Ctx& ctx) {
   if (valid) {
     const cplx<T>* in = (const cplx<T>*)((const T*)d.in + (long long)a * d.inStrideA + (long long)b * d.inStrideB);
     pass_foreach<S, 0>(v, t, [&](int i, cplx<T>& r) { r = ld_g<Ctx>(d, in + i); });
+    if constexpr (ctx_ring<Ctx>::value) ctx.after_loads();
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
-  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { group_sync<S::G, PC>(ctx, pcl); });
   cplx<T>* stage = (cplx<T>*)ctx.smem() + ((PC * S::SMEM_ELEMS + 1) & ~1);   // only touched when d.staged
   // publish Z so every thread can read its mirror partner Z[M-k]
-  if constexpr (S::NP > 1) ctx.sync();
+  if constexpr (S::NP > 1) group_sync<S::G, PC>(ctx, pcl);
   pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { sm[S::phys(k)] = r; });
-  ctx.sync();
+  group_sync<S::G, PC>(ctx, pcl);
   if (valid) {
     constexpr int RL = S::radix(S::NP - 1), NBL = S::nb(S::NP - 1), CNTL = S::cnt(S::NP - 1);
     const SegDst& s0 = d.seg[0];
@@ -698,6 +722,7 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
         const int i = t + q * S::G;
         if (i <= M) x[q] = ld_g<Ctx>(d, in + i);
       }
+      if constexpr (ctx_ring<Ctx>::value) ctx.after_loads();
       if constexpr (GEN) {
         if (d.op != OP_NONE) {
           const OpCol col = op_prepare(d, a, b);
@@ -715,7 +740,7 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
       if (i <= M) sm[S::phys(i)] = x[q];
     }
   }
-  ctx.sync();
+  group_sync<S::G, PC>(ctx, pcl);
   cplx<T> v[S::NREG];
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
@@ -745,8 +770,8 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
       });
     }
   }
-  ctx.sync();
-  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { ctx.sync(); });
+  group_sync<S::G, PC>(ctx, pcl);
+  fft_passes<S>(v, t, w1, [&](int i) { return sm + S::phys(i); }, [&]() { group_sync<S::G, PC>(ctx, pcl); });
   if (valid) {
     const SegDst& sd = d.seg[0];
     cplx<T>* out = (cplx<T>*)((T*)sd.base + (long long)a * sd.strideA + (long long)b * sd.strideB);

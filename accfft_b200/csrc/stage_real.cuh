@@ -151,6 +151,18 @@ ACC_HD void strided_c2r_body(const StageDesc& d, Ctx& ctx) {
     pass_foreach<S, S::NP - 1>(v, t, [&](int n, cplx<T>& r) { store_real_pair(d, cswap(r), n, a, b0, valid1); });
 }
 
+// i * k * scale for transform index k of a derivative stage (OP_GRAD along the transform axis, per-axis scheme: the mode
+// pair +-floor(N/2) vanishes as a pair) -- the inline special case of op_weight / apply_op (stage.cuh), in the kernel's own
+// precision: no call and no double-precision arithmetic per element in the single-precision kernels
+template <class T>
+ACC_HD cplx<T> deriv_mul(const StageDesc& d, cplx<T> v, int k) {
+  const int N = d.n[d.opAxis];
+  const int X = k + d.off[d.opAxis];
+  const int kw = (X == N / 2 || X == N - N / 2) ? 0 : (X > N / 2 ? X - N : X);
+  const T w = T(d.scale) * T(kw);
+  return {-(w * v.y), w * v.x};
+}
+
 // ================================================================================================
 // strided spectral derivative: real -> forward passes -> multiply by the symbol (d.op, on the FULL axis) -> inverse
 // passes -> real, one read and one write of the field.  Replaces r2c + grad_mult_wave_number{x,y} + c2r of
@@ -174,17 +186,16 @@ ACC_HD void strided_deriv_body(const StageDesc& d, Ctx& ctx) {
   cplx<T>* sm = (cplx<T>*)ctx.smem();
   auto addr = [&](int i) { return sm + S::phys(i) * TC + c; };
   fft_passes<S>(v, t, w1, addr, [&]() { ctx.sync(); });
-  const OpCol col = op_prepare_if(d, a, b0);   // (the derivative runs along the transform axis: nothing column dependent)
   // symbol multiply in output order (index j + r*N/R_last).  When the first and the last radix agree that IS the pass-0
   // gather order of the inverse (index j + r*N/R_0), so the registers go straight into the second set of passes;
   // otherwise they are re-ordered through the tile.  (swapped: inverse = swap . forward . swap)
   constexpr bool kSameOrder = S::radix(0) == S::radix(S::NP - 1);
   if constexpr (kSameOrder) {
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(apply_op(d, col, r, k)); });
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(deriv_mul(d, r, k)); });
     if constexpr (S::NP > 1) ctx.sync();   // the forward's last gathers are done before the inverse scatters again
   } else {
     if constexpr (S::NP > 1) ctx.sync();
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(apply_op(d, col, r, k)); });
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(deriv_mul(d, r, k)); });
     ctx.sync();
     pass_gather<S, 0>(v, t, addr);
     if constexpr (S::NP > 1) ctx.sync();
@@ -222,20 +233,19 @@ ACC_HD void contig_deriv_body(const StageDesc& d, Ctx& ctx) {
   }
   cplx<T>* sm = (cplx<T>*)ctx.smem() + pcl * S::SMEM_ELEMS;
   auto addr = [&](int i) { return sm + S::phys(i); };
-  fft_passes<S>(v, t, w1, addr, [&]() { ctx.sync(); });
-  const OpCol col = op_prepare_if(d, a0, b0);
+  fft_passes<S>(v, t, w1, addr, [&]() { group_sync<S::G, PC>(ctx, pcl); });
   constexpr bool kSameOrder = S::radix(0) == S::radix(S::NP - 1);
   if constexpr (kSameOrder) {
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(apply_op(d, col, r, k)); });
-    if constexpr (S::NP > 1) ctx.sync();
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { r = cswap(deriv_mul(d, r, k)); });
+    if constexpr (S::NP > 1) group_sync<S::G, PC>(ctx, pcl);
   } else {
-    if constexpr (S::NP > 1) ctx.sync();
-    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(apply_op(d, col, r, k)); });
-    ctx.sync();
+    if constexpr (S::NP > 1) group_sync<S::G, PC>(ctx, pcl);
+    pass_foreach<S, S::NP - 1>(v, t, [&](int k, cplx<T>& r) { *addr(k) = cswap(deriv_mul(d, r, k)); });
+    group_sync<S::G, PC>(ctx, pcl);
     pass_gather<S, 0>(v, t, addr);
-    if constexpr (S::NP > 1) ctx.sync();
+    if constexpr (S::NP > 1) group_sync<S::G, PC>(ctx, pcl);
   }
-  fft_passes<S>(v, t, w1, addr, [&]() { ctx.sync(); });
+  fft_passes<S>(v, t, w1, addr, [&]() { group_sync<S::G, PC>(ctx, pcl); });
   if (valid0) {
     const SegDst& sd = d.seg[0];
     T* o0 = (T*)sd.base + (long long)a0 * sd.strideA + (long long)b0 * sd.strideB;

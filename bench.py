@@ -517,6 +517,23 @@ def main():
     # transfers of what the stage packed)
     nvl = {"fwd_z": C0 * (dims[1] - 1) / dims[1], "fwd_y": C1 * (dims[0] - 1) / dims[0],
            "inv_x": C2 * (dims[0] - 1) / dims[0], "inv_y": C0 * (dims[1] - 1) / dims[1]}
+    # The fused local pair (csrc/fused.cuh): Z and Y of a direction run as ONE persistent kernel, profiled in the slot of its
+    # first pass; the array between the two passes is a ring of a few planes that stays in L2.  Its ALGORITHMIC bytes stay
+    # those of the two passes (every pass reads and writes its array once); the HBM floor of the kernel is lower by
+    # the write + read of the intermediate, so "gbs" of a fused stage may exceed the HBM peak -- hbm_min_bytes says by how much.
+    fused = {"forward": plan.fused_info(False), "inverse": plan.fused_info(True)}
+    hbm_min = {}
+    if fused["forward"] and prof.get("fwd_y", (0, 0))[1] == 0:
+        algo["fwd_zy"] = algo.pop("fwd_z") + algo.pop("fwd_y")
+        hbm_min["fwd_zy"] = R + C1
+        prof["fwd_zy"] = prof.pop("fwd_z")
+        if "fwd_y" in nvl:
+            nvl["fwd_zy"] = nvl.pop("fwd_y")
+    if fused["inverse"] and prof.get("inv_z", (0, 0))[1] == 0:
+        algo["inv_yz"] = algo.pop("inv_y") + algo.pop("inv_z")
+        hbm_min["inv_yz"] = C1 + R
+        prof["inv_yz"] = prof.pop("inv_y")
+        nvl.pop("inv_y", None)
     xmode = plan.exchange_mode()
     exchange = dict(xmode)
     if xmode["mode"] == "copy_engine":
@@ -539,6 +556,9 @@ def main():
             if k in algo:
                 stages[k]["algo_bytes"] = algo[k]
                 stages[k]["gbs"] = algo[k] / (tms / args.steps * 1e-3) / 1e9     # per-step bytes / per-step time
+            if k in hbm_min:
+                stages[k]["hbm_min_bytes"] = hbm_min[k]
+                stages[k]["hbm_min_gbs"] = hbm_min[k] / (tms / args.steps * 1e-3) / 1e9
             if nvl.get(k):
                 stages[k]["nvlink_out_bytes"] = int(nvl[k])
                 stages[k]["nvlink_out_gbs"] = nvl[k] / (tms / args.steps * 1e-3) / 1e9
@@ -557,6 +577,13 @@ def main():
                                   "capture (profiles/traffic.json); not re-measured in this run" if traffic else None,
                 "algo_bytes_per_launch": algo[dom] / stages[dom]["launches_per_step"],
                 "ms_per_launch": stages[dom]["ms"], "peak_source": peak_src}
+    if dom in hbm_min:
+        roofline.update({"hbm_min_bytes_per_launch": hbm_min[dom] / stages[dom]["launches_per_step"],
+                         "hbm_min_frac": stages[dom]["hbm_min_gbs"] / peak,
+                         "note": "fused Z+Y persistent kernel: algorithmic bytes = both passes read and write their array once "
+                                 "(SURVEY 8d); the array between the passes lives in an L2-resident ring, so the kernel's HBM "
+                                 "floor is hbm_min_bytes and `frac` may exceed 1 -- hbm_min_frac is the fraction of the HBM peak "
+                                 "its unavoidable traffic reaches"})
     if "nvlink_out_gbs" in stages[dom]:
         # the dominant kernel stores to peers (exchange fused into the FFT kernel): its ceiling is the link, not HBM
         roofline.update({"bound": "nvlink", "achieved": stages[dom]["nvlink_out_gbs"], "peak": NVLINK_GBS,
@@ -618,7 +645,7 @@ def main():
                        ((R + 2 * C0) / 1e9), "round_trip_rel_l2": rt_err},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "stages": stages, "step_roofline": step_roof,
-            "stage_kernels": stage_kernels, "exchange": exchange, "gpu_copies": int(copies),
+            "stage_kernels": stage_kernels, "fused_pair": fused, "exchange": exchange, "gpu_copies": int(copies),
             "parity": parity, "configs": configs,
         }
         print(json.dumps(line), flush=True)

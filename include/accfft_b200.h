@@ -107,6 +107,17 @@ int accfftb_plan_ipc_import(accfftb_plan* plan, const void* blobs, int nblobs);
  * handles instead of IPC blobs; peer access is enabled with cudaDeviceEnablePeerAccess. */
 int accfftb_plan_attach_local_peers(accfftb_plan* plan, accfftb_plan* const* plans, int nplans);
 
+/* Batched fields.  The reference's exchange has a `howmany` path for several fields at once
+ * (fast_transpose_cuda_v2_h etc., src/transpose_gpu.cpp:4454-4726, T_Plan_gpu::execute_gpu(..., howmany), :3808-4021) that its
+ * plans never use; FFTW calls the same thing a "many" plan.  A plan made with howmany > 1 owns howmany sets of exchange
+ * buffers per rank (memory: howmany x the single-field plan) and accepts up to howmany fields per accfftb_execute_*_many
+ * call: every stage runs for all fields back to back and the fields SHARE the inter-GPU barriers -- one synchronisation
+ * per exchange for the whole batch instead of one per field.  On such a plan the full-3-D gradient / divergence
+ * (accfftb_grad_slow / accfftb_divergence_slow) send their three components through one set of exchanges as well.
+ * Everything else about the plan is unchanged (single-field calls use field set 0). */
+accfftb_plan* accfftb_plan_create_many(const int n[3], const int c_dims[2], int rank, int kind, int prec, unsigned flags, int howmany);
+int accfftb_plan_howmany(const accfftb_plan* plan);
+
 /* CUDA stream (cudaStream_t) the plan's kernels are enqueued on; default: the legacy default stream,
  * as in the reference.  blocking = 1 (default) makes every execute / operator call return only when
  * the device has finished, like the reference (cudaDeviceSynchronize, src/accfft_gpu.cpp:620);
@@ -139,7 +150,10 @@ int accfftb_plan_stage_variant(const accfftb_plan* plan, int slot);
  * of a few planes that stays in L2 and never reaches HBM; the launch is profiled in the slot of its first pass (0 forward,
  * 4 inverse).  dir: 0 forward, 1 inverse.  info (may be NULL) receives what the last such launch used:
  * {planes per chunk, lag, ring slots, chunks, ring planes (0 = whole buffer), grid, threads, shared memory bytes}.
- * Returns 1 if the last transform in that direction ran fused, 0 if not (ACCFFT_B200_FUSED=0 switches it off). */
+ * Returns 1 if the last transform in that direction ran fused, 0 if not.  The fused kernel is OFF by default
+ * (ACCFFT_B200_FUSED=1 at plan creation switches it on): it removes the HBM traffic of the intermediate array as designed
+ * (ncu: 2.2 GB instead of 4.3 GB per direction at 512^3 double) but its tiles run slower inside the persistent loop than as
+ * stand-alone kernels -- 0.94 ms vs 0.74 ms per direction; DESIGN.md section 4 has the measurements. */
 int accfftb_plan_fused_info(const accfftb_plan* plan, int dir, int info[8]);
 
 long long accfftb_plan_alloc_max(const accfftb_plan* plan);
@@ -187,6 +201,13 @@ int accfftb_execute_r2c(accfftb_plan* plan, const void* data, void* data_out, do
 int accfftb_execute_c2r(accfftb_plan* plan, const void* data, void* data_out, double* timer, int xyz);
 /* accfft_execute_c2c_gpu / _gpuf (:943-1136): direction = ACCFFTB_FORWARD / ACCFFTB_BACKWARD. */
 int accfftb_execute_c2c(accfftb_plan* plan, int direction, const void* data, void* data_out, double* timer, int xyz);
+
+/* Batched executes on a plan made with accfftb_plan_create_many: howmany (<= the plan's field count) independent fields,
+ * data[f] -> data_out[f], all axes, out of place.  Result = howmany single-field executes; the stages of all fields share
+ * the inter-GPU barriers (see accfftb_plan_create_many).  Collective like the single-field calls. */
+int accfftb_execute_r2c_many(accfftb_plan* plan, int howmany, const void* const* data, void* const* data_out, double* timer);
+int accfftb_execute_c2r_many(accfftb_plan* plan, int howmany, const void* const* data, void* const* data_out, double* timer);
+int accfftb_execute_c2c_many(accfftb_plan* plan, int direction, int howmany, const void* const* data, void* const* data_out, double* timer);
 
 /* ---- single-axis real transforms: accfft_execute_{r2c,c2r}_{x,y,z}_gpu_t (src/accfft_gpu.cpp:1212-1604), the
  * building blocks of the reference's per-axis gradient.  r2c plans only.  axis: 0 = x, 1 = y, 2 = z.

@@ -64,10 +64,21 @@ def run(n, single, r2c, iters=10):
     C = n[0] * n[1] * n2c * cs
     algo = {"fwd_z": R + C if r2c else 2 * C, "fwd_y": 2 * C, "fwd_x": 2 * C, "inv_x": 2 * C, "inv_y": 2 * C, "inv_z": C + R if r2c else 2 * C}
     tot = sum(algo.values())
+    # fused local pair (csrc/fused.cuh): one kernel, profiled in the slot of its first pass
+    order = ["fwd_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "inv_z"]
+    if p.fused_info(False) and prof["fwd_y"][1] == 0:
+        algo["fwd_zy"] = algo["fwd_z"] + algo["fwd_y"]
+        prof["fwd_zy"] = prof["fwd_z"]
+        order[0:2] = ["fwd_zy"]
+    if p.fused_info(True) and prof["inv_z"][1] == 0:
+        algo["inv_yz"] = algo["inv_y"] + algo["inv_z"]
+        prof["inv_yz"] = prof["inv_y"]
+        order[-2:] = ["inv_yz"]
     print("%s %s %s: round trip %.3f ms, %.0f GB/s algorithmic = %.3f of %.0f; kernels %s" %
           ("x".join(map(str, n)), "single" if single else "double", "r2c" if r2c else "c2c", ms, tot / ms / 1e6, tot / ms / 1e6 / PEAK, PEAK,
            p.stage_kernels()))
-    for k in ("fwd_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "inv_z"):
+    print("   fused pair: forward %s, inverse %s" % (p.fused_info(False), p.fused_info(True)))
+    for k in order:
         t, c = prof[k]
         if c:
             tp = t / iters   # per step (a stage may run as several chunk launches)

@@ -144,6 +144,7 @@ struct EmuWorld {
   std::vector<EmuBackend> be;
   std::vector<Plan> plans;
   std::vector<std::vector<char>> bufA, bufB, bufA2, bufB2, spec;
+  std::vector<long long> strides;   // batched plans: bytes between the field sets of a rank's buffers
   pthread_barrier_t bar;
 };
 int EmuBackend::barrier() {
@@ -180,7 +181,15 @@ void* emu_world_create(const int* n, int P0, int P1, int r2c, int prec) {
     p.be = &w->be[r];
     p.nprocs = w->nprocs;
     // +64 bytes so that out-of-range writes are more likely to be caught by the canary check below
-    const size_t bb = (size_t)Plan::buffer_bytes(w->n, w->np, coords, w->r2c, w->prec, w->nprocs);
+    const size_t bb1 = (size_t)Plan::buffer_bytes(w->n, w->np, coords, w->r2c, w->prec, w->nprocs);
+    // batched plans (EMU_BATCH=<fields>): every buffer holds `batch` field sets, one every `stride` bytes
+    const char* benv = getenv("EMU_BATCH");
+    const int batch = benv ? std::max(1, atoi(benv)) : 1;
+    const size_t stride = (bb1 + 255) / 256 * 256;
+    const size_t bb = batch > 1 ? stride * (size_t)batch : bb1;
+    p.batch = batch;
+    w->strides.resize(w->nprocs);
+    w->strides[r] = (long long)stride;
     w->bufA[r].assign(bb + 64, (char)0xEE);
     w->bufB[r].assign(bb + 64, (char)0xEE);
     w->bufA2[r].assign(bb + 64, (char)0xEE);
@@ -200,6 +209,7 @@ void* emu_world_create(const int* n, int P0, int P1, int r2c, int prec) {
         p.peerB_alt.push_back(w->bufB2[q].data());
       }
     }
+    if (p.batch > 1) p.field_stride = w->strides;
     if (!p.check_supported()) {
       fprintf(stderr, "emul: %s\n", p.error.c_str());
       delete w;
@@ -242,6 +252,25 @@ int emu_execute(void* h, int mode, void** in, void** out, int padded) {
       else rc[r] = p.execute_spectral(in[r], out[r], OP_BIHARMONIC, w->spec[r].data());
     });
   }
+  for (auto& t : th) t.join();
+  for (int r = 0; r < w->nprocs; ++r)
+    if (rc[r]) return rc[r];
+  return canaries_ok(w) ? 0 : -99;
+}
+
+// batched fields: in / out are [field][rank] pointer tables flattened field-major; mode 0 forward, 1 inverse
+int emu_execute_many(void* h, int mode, int nf, void** in, void** out) {
+  EmuWorld* w = (EmuWorld*)h;
+  std::vector<std::thread> th;
+  std::vector<int> rc(w->nprocs, 0);
+  for (int r = 0; r < w->nprocs; ++r)
+    th.emplace_back([&, r]() {
+      std::vector<const void*> ins(nf);
+      std::vector<void*> outs(nf);
+      for (int f = 0; f < nf; ++f) ins[f] = in[f * w->nprocs + r], outs[f] = out[f * w->nprocs + r];
+      Plan& p = w->plans[r];
+      rc[r] = mode == 0 ? p.execute_forward_many(nf, ins.data(), outs.data(), false) : p.execute_inverse_many(nf, ins.data(), outs.data(), false);
+    });
   for (auto& t : th) t.join();
   for (int r = 0; r < w->nprocs; ++r)
     if (rc[r]) return rc[r];

@@ -70,6 +70,8 @@ def lib():
         _lib.emu_execute_xyz.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
                                          ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         pp = ctypes.POINTER(ctypes.c_void_p)
+        _lib.emu_execute_many.restype = ctypes.c_int
+        _lib.emu_execute_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, pp, pp]
         _lib.emu_execute_grad.restype = ctypes.c_int
         _lib.emu_execute_grad.argtypes = [ctypes.c_void_p, pp, pp, pp, pp, ctypes.c_int]
         _lib.emu_execute_div.restype = ctypes.c_int
@@ -170,6 +172,57 @@ class World:
             else:
                 blocks.append(outs[r].view(self.cdt)[:s0 * s1 * n[2]].reshape(s0, s1, n[2]).copy())
         return blocks
+
+    def forward_many(self, xs_global):
+        """batched forward transforms of several global fields (worlds made under EMU_BATCH >= len(xs_global))"""
+        n, nf = self.n, len(xs_global)
+        ins, outs = [], []
+        for x_global in xs_global:
+            ins.append([np.ascontiguousarray(orc.local_input(x_global, n, self.np_, self.coords(r)).astype(self.rdt if self.r2c else self.cdt))
+                        for r in range(self.nprocs)])
+            outs.append(self.alloc_out())
+        pin = (ctypes.c_void_p * (nf * self.nprocs))(*[a.ctypes.data for f in ins for a in f])
+        pout = (ctypes.c_void_p * (nf * self.nprocs))(*[a.ctypes.data for f in outs for a in f])
+        rc = lib().emu_execute_many(self.h, 0, nf, pin, pout)
+        if rc:
+            raise RuntimeError(f"emu_execute_many rc={rc}")
+        n2c = n[2] // 2 + 1 if self.r2c else n[2]
+        res = []
+        for f in range(nf):
+            blocks = []
+            for r in range(self.nprocs):
+                c = self.coords(r)
+                s1 = orc.block(n[1], self.np_[0], c[0])[0]
+                s2 = orc.block(n2c, self.np_[1], c[1])[0]
+                blocks.append(outs[f][r].view(self.cdt)[:n[0] * s1 * s2].reshape(n[0], s1, s2).copy())
+            res.append(blocks)
+        return res
+
+    def inverse_many(self, Xs_global):
+        n, nf = self.n, len(Xs_global)
+        ins, outs = [], []
+        for X_global in Xs_global:
+            ins.append([np.ascontiguousarray(orc.local_output(X_global, n, self.np_, self.coords(r), r2c=self.r2c).astype(self.cdt))
+                        for r in range(self.nprocs)])
+            outs.append(self.alloc_out())
+        pin = (ctypes.c_void_p * (nf * self.nprocs))(*[a.ctypes.data for f in ins for a in f])
+        pout = (ctypes.c_void_p * (nf * self.nprocs))(*[a.ctypes.data for f in outs for a in f])
+        rc = lib().emu_execute_many(self.h, 1, nf, pin, pout)
+        if rc:
+            raise RuntimeError(f"emu_execute_many rc={rc}")
+        res = []
+        for f in range(nf):
+            blocks = []
+            for r in range(self.nprocs):
+                c = self.coords(r)
+                s0 = orc.block(n[0], self.np_[0], c[0])[0]
+                s1 = orc.block(n[1], self.np_[1], c[1])[0]
+                if self.r2c:
+                    blocks.append(outs[f][r][:s0 * s1 * n[2]].reshape(s0, s1, n[2]).copy())
+                else:
+                    blocks.append(outs[f][r].view(self.cdt)[:s0 * s1 * n[2]].reshape(s0, s1, n[2]).copy())
+            res.append(blocks)
+        return res
 
     def spectral(self, x_global, op):
         n = self.n

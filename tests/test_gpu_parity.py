@@ -636,10 +636,8 @@ def test_timer_accumulates_and_launch_count(cuda_device):
     back = torch.zeros_like(x)
     p.execute_c2r(out, back)
     prof = p.profile_read()
-    # the local Z / Y pair runs as one fused kernel at this size: it is profiled in the slot of its first pass
-    assert p.fused_info(False) is not None and p.fused_info(True) is not None
-    assert all(prof[k][1] == 1 and prof[k][0] > 0 for k in ("fwd_z", "fwd_x", "inv_x", "inv_y"))
-    assert prof["fwd_y"][1] == 0 and prof["inv_z"][1] == 0
+    assert p.fused_info(False) is None and p.fused_info(True) is None   # the fused local pair is opt-in (ACCFFT_B200_FUSED=1)
+    assert all(prof[k][1] == 1 and prof[k][0] > 0 for k in ("fwd_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "inv_z"))
     assert prof["barrier"][1] == 0
     p.destroy()
 
@@ -894,7 +892,7 @@ def test_double_buffered_exchange_mixed_operations(cuda_device, monkeypatch, n, 
 
 
 # ---- fused local Z / Y pair (csrc/fused.cuh): one persistent kernel, intermediate planes in an L2-resident ring ----------
-FUSED_CASES = [((64, 64, 64), True, False), ((64, 64, 64), True, True), ((40, 128, 128), True, False), ((24, 256, 256), True, True),
+FUSED_CASES = [((256, 256, 256), True, False), ((64, 64, 64), True, False), ((64, 64, 64), True, True), ((40, 128, 128), True, False), ((24, 256, 256), True, True),
                ((37, 64, 64), True, False), ((64, 64, 64), False, False), ((20, 128, 128), False, True), ((3, 512, 512), True, False)]
 
 
@@ -948,7 +946,10 @@ def test_fused_local_pair_matches_separate_kernels(cuda_device, monkeypatch, n, 
         for k in ("CP", "LAG", "NS"):
             monkeypatch.delenv("ACCFFT_B200_FUSED_" + k, raising=False)
     for a, b in zip(res["fused"], res["separate"]):
-        assert np.array_equal(a, b)
+        if single:   # the stand-alone single-precision Z kernels run their own schedules (schedules.def: KEEP_FC): same accuracy, not the same bits
+            assert orc.rel_l2(a, b) <= 2e-6
+        else:
+            assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("n,dims,r2c,single", [((64, 64, 64), (2, 1), True, False), ((64, 64, 64), (4, 1), True, True),
@@ -963,6 +964,7 @@ def test_fused_local_pair_on_slab_grids_threads(cuda_device, monkeypatch, n, dim
     rdt, cdt = dtypes(single)
     tdt = torch.float32 if single else torch.float64
     es = 4 if single else 8
+    monkeypatch.setenv("ACCFFT_B200_FUSED", "1")
     if ring == "tiny":
         for k, v in (("CP", "1"), ("LAG", "1"), ("NS", "2")):
             monkeypatch.setenv("ACCFFT_B200_FUSED_" + k, v)
