@@ -706,55 +706,51 @@ ACC_HD void contig_c2r_body(const StageDesc& d, Ctx& ctx) {
   constexpr int R0 = S::radix(0), NB0 = S::nb(0), CNT0 = S::cnt(0);
   cplx<T> w1[S::NTW];
   load_base_twiddles<S, 2>(w1, t, tw);
-  cplx<T> ws[CNT0];
-  ACC_UNROLL
-  for (int u = 0; u < CNT0; ++u) ws[u] = tw[(t + u * S::G) % M];
-  {
-    // stage the M+1 input coefficients in shared memory (all global loads issued before the first use)
-    constexpr int NLD = (M + 1 + S::G - 1) / S::G;
-    cplx<T> x[NLD];
+  // twiddles W_N2^j of the pre-processing step: fetched up front (the fetch overlaps the data loads) when that costs at most
+  // eight registers, else where they are used (the table is L1-resident; measured: the 128- and 1024-point double kernels
+  // spill otherwise, the 256-point one loses 5 % when it fetches late)
+  constexpr bool WS_EARLY = CNT0 * (int)sizeof(cplx<T>) <= 32;
+  cplx<T> ws[WS_EARLY ? CNT0 : 1];
+  if constexpr (WS_EARLY) {
     ACC_UNROLL
-    for (int q = 0; q < NLD; ++q) x[q] = {T(0), T(0)};
-    if (valid) {
-      const cplx<T>* in = (const cplx<T>*)d.in + (long long)ring_in<Ctx>(d, a) * d.inStrideA + (long long)b * d.inStrideB;
-      ACC_UNROLL
-      for (int q = 0; q < NLD; ++q) {
-        const int i = t + q * S::G;
-        if (i <= M) x[q] = ld_g<Ctx>(d, in + i);
-      }
-      if constexpr (ctx_ring<Ctx>::value) ctx.after_loads();
-      if constexpr (GEN) {
-        if (d.op != OP_NONE) {
-          const OpCol col = op_prepare(d, a, b);
-          ACC_UNROLL
-          for (int q = 0; q < NLD; ++q) {
-            const int i = t + q * S::G;
-            if (i <= M) x[q] = apply_op(d, col, x[q], i);
-          }
-        }
-      }
-    }
-    ACC_UNROLL
-    for (int q = 0; q < NLD; ++q) {
-      const int i = t + q * S::G;
-      if (i <= M) sm[S::phys(i)] = x[q];
-    }
+    for (int u = 0; u < CNT0; ++u) ws[u] = tw[(t + u * S::G) % M];
   }
-  group_sync<S::G, PC>(ctx, pcl);
+  // The M + 1 input coefficients: every thread loads the ones it needs as X[k] -- the operands of pass 0, k = j + r NB0, all
+  // loads issued before the first use -- keeps them in registers and publishes them to shared memory, from which it then
+  // only fetches the mirror partners X[M - k] (X[M], the partner of k = 0, is loaded by the first thread of the pencil).
   cplx<T> v[S::NREG];
   ACC_UNROLL
   for (int i = 0; i < S::NREG; ++i) v[i] = {T(0), T(0)};
+  cplx<T> xM = {T(0), T(0)};
+  if (valid) {
+    const cplx<T>* in = (const cplx<T>*)d.in + (long long)ring_in<Ctx>(d, a) * d.inStrideA + (long long)b * d.inStrideB;
+    pass_foreach<S, 0>(v, t, [&](int k, cplx<T>& r) { r = ld_g<Ctx>(d, in + k); });
+    if (t == 0) xM = ld_g<Ctx>(d, in + M);
+    if constexpr (ctx_ring<Ctx>::value) ctx.after_loads();
+    if constexpr (GEN) {
+      if (d.op != OP_NONE) {
+        const OpCol col = op_prepare(d, a, b);
+        pass_foreach<S, 0>(v, t, [&](int k, cplx<T>& r) { r = apply_op(d, col, r, k); });
+        if (t == 0) xM = apply_op(d, col, xM, M);
+      }
+    }
+  }
+  pass_foreach<S, 0>(v, t, [&](int k, cplx<T>& r) { sm[S::phys(k)] = r; });
+  if (t == 0) sm[S::phys(M)] = xM;
+  group_sync<S::G, PC>(ctx, pcl);
   // Z'[k] = (X[k] + conj(X[M-k])) + i conj(W_N2^k) (X[k] - conj(X[M-k])) for k = j + r*NB0, with
   // W_N2^k = W_N2^j * W_(2 R0)^r (compile-time second factor)
   ACC_UNROLL
   for (int u = 0; u < CNT0; ++u) {
     const int j = t + u * S::G;
     if (CNT0 * S::G == NB0 || j < NB0) {
-      const cplx<T> wj = ws[u];
+      cplx<T> wj;
+      if constexpr (WS_EARLY) wj = ws[u];
+      else wj = tw[j % M];
       static_for<0, R0>([&](auto rc) {
         constexpr int r = decltype(rc)::value;
         const int k = j + r * NB0;
-        const cplx<T> A = sm[S::phys(k)];
+        const cplx<T> A = v[u * R0 + r];
         const cplx<T> B = sm[S::phys(M - k)];
         cplx<T> z;
         if (r == 0 && k == 0) {

@@ -312,6 +312,55 @@ def config_entry(acc, torch, dist, dev, world, rank, name, n, dims, r2c, single,
     return e
 
 
+def batched_entry(acc, torch, dist, dev, world, rank, n, dims, nf=3, iters=5):
+    """nf fields (a vector field) through ONE set of exchanges (accfftb_execute_*_many) vs nf single-field round trips
+    on the same plan; plus the full-3-D gradient / divergence, which batch their components on such a plan, vs a one-field plan"""
+    comm = acc.accfft_create_comm(list(dims), rank=rank, nprocs=world)
+    p = acc.Plan(n, comm, r2c=True, single=False, howmany=nf)
+    isz = p.isize
+    cnt = max(isz[0] * isz[1] * isz[2], 2)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    xs = [torch.rand(cnt, dtype=torch.float64, device=dev, generator=gen) * 2 - 1 for _ in range(nf)]
+    outs = [torch.zeros(max(p.alloc_max // 8, 2), dtype=torch.float64, device=dev) for _ in range(nf)]
+    backs = [torch.zeros_like(x) for x in xs]
+    p.set_stream(torch.cuda.current_stream().cuda_stream)
+    p.set_blocking(False)
+
+    def seq():
+        for f in range(nf):
+            p.execute_r2c(xs[f], outs[f])
+            p.execute_c2r(outs[f], backs[f])
+
+    def many():
+        p.execute_r2c_many(xs, outs)
+        p.execute_c2r_many(outs, backs)
+
+    ms_seq = time_plan(torch, dist, dev, world, seq, iters)
+    ref = [b.clone() for b in backs]
+    for b in backs:
+        b.zero_()
+    ms_many = time_plan(torch, dist, dev, world, many, iters)
+    same = all(bool(torch.equal(a, b)) for a, b in zip(ref, backs))
+    div = torch.zeros_like(xs[0])
+    g = [torch.zeros_like(xs[0]) for _ in range(3)]
+    e = {"grid": "%dx%d" % dims, "fields": nf, "ms_sequential": ms_seq, "ms_batched": ms_many, "speedup": ms_seq / ms_many,
+         "bitwise_equal": same, "ok": same}
+    if nf >= 3:
+        e["grad3d_batched_ms"] = time_plan(torch, dist, dev, world, lambda: p.grad_slow(g[0], g[1], g[2], xs[0]), iters)
+        e["div3d_batched_ms"] = time_plan(torch, dist, dev, world, lambda: p.divergence_slow(div, xs[0], xs[1], xs[2]), iters)
+    p.destroy()
+    if nf >= 3:
+        p1 = acc.Plan(n, comm, r2c=True, single=False)
+        p1.set_stream(torch.cuda.current_stream().cuda_stream)
+        p1.set_blocking(False)
+        e["grad3d_ms"] = time_plan(torch, dist, dev, world, lambda: p1.grad_slow(g[0], g[1], g[2], xs[0]), iters)
+        e["div3d_ms"] = time_plan(torch, dist, dev, world, lambda: p1.divergence_slow(div, xs[0], xs[1], xs[2]), iters)
+        p1.destroy()
+    del xs, outs, backs, ref
+    torch.cuda.empty_cache()
+    return e
+
+
 def run_configs(acc, torch, dist, dev, world, rank, peak):
     slab, pencil = (world, 1), tuple(PENCIL.get(world, (world, 1)))
     grids = [pencil] + ([slab] if slab != pencil else [])
@@ -327,6 +376,14 @@ def run_configs(acc, torch, dist, dev, world, rank, peak):
             except Exception as ex:   # a config that does not fit (memory) is reported, not fatal for the headline line
                 out[name].append({"grid": "%dx%d" % dims, "error": repr(ex)[:200]})
                 torch.cuda.empty_cache()
+    name = "batched fields: 3 x 512^3 double r2c + c2r through one set of exchanges (accfftb_execute_*_many) vs one by one"
+    out[name] = []
+    for dims in grids:
+        try:
+            out[name].append(batched_entry(acc, torch, dist, dev, world, rank, (512, 512, 512), dims))
+        except Exception as ex:
+            out[name].append({"grid": "%dx%d" % dims, "error": repr(ex)[:200]})
+            torch.cuda.empty_cache()
     return out
 
 
@@ -416,12 +473,11 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
-    plan.set_profiling(True)
-    plan.profile_read()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = plan.launch_count
     copies0 = plan.copy_count
     sync_all()
+    # the timed region: EXACTLY args.steps steps between two events on the plan's stream, nothing else enqueued
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(args.steps):
@@ -431,6 +487,15 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = plan.launch_count - launches0
     copies = plan.copy_count - copies0
+    # per-kernel durations for the roofline: the same args.steps steps once more, this time with an event pair around every
+    # launch (accfftb_plan_set_profiling).  Kept out of the region above because the 12 extra event records per step keep
+    # consecutive kernels from running back to back (measured: +3 % on the step).
+    plan.set_profiling(True)
+    plan.profile_read()
+    with torch.cuda.stream(stream):
+        for _ in range(args.steps):
+            step()
+    sync_all()
     prof = plan.profile_read()
     plan.set_profiling(False)
     if world > 1:
@@ -576,7 +641,9 @@ def main():
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, one --set full "
                                   "capture (profiles/traffic.json); not re-measured in this run" if traffic else None,
                 "algo_bytes_per_launch": algo[dom] / stages[dom]["launches_per_step"],
-                "ms_per_launch": stages[dom]["ms"], "peak_source": peak_src}
+                "ms_per_launch": stages[dom]["ms"], "peak_source": peak_src,
+                "timing": "CUDA event pair around every launch of a second pass over the same %d steps, on the plan's stream "
+                          "(the timed region behind `value` carries no per-launch events)" % args.steps}
     if dom in hbm_min:
         roofline.update({"hbm_min_bytes_per_launch": hbm_min[dom] / stages[dom]["launches_per_step"],
                          "hbm_min_frac": stages[dom]["hbm_min_gbs"] / peak,

@@ -1012,3 +1012,95 @@ def test_fused_local_pair_on_slab_grids_threads(cuda_device, monkeypatch, n, dim
     for p in plans:
         acc.lib().accfftb_plan_destroy(p._h)
         p._h = None
+
+
+# ---- batched fields (accfftb_plan_create_many / accfftb_execute_*_many) ---------------------------------------------------
+@pytest.mark.parametrize("n,dims,r2c,single", [((64, 48, 40), (1, 1), True, False), ((16, 12, 20), (2, 2), True, False),
+                                               ((5, 6, 6), (4, 1), True, False), ((64, 48, 40), (2, 2), True, True),
+                                               ((16, 12, 20), (2, 2), False, False), ((3, 5, 4), (4, 2), True, False)])
+def test_batched_fields_equal_single_field_transforms(cuda_device, n, dims, r2c, single):
+    """three fields through one set of exchanges = three single-field executes, bitwise (same kernels, same order per field);
+    ranks as host threads on cuda:0; the 3-D gradient / divergence batch their components on such a plan"""
+    torch = torch_mod()
+    nprocs = dims[0] * dims[1]
+    rdt, cdt = dtypes(single)
+    tdt = torch.float32 if single else torch.float64
+    es = 4 if single else 8
+    nf = 3
+    xs = [orc.synthetic_real(n, 70 + f) if r2c else orc.synthetic_complex(n, 70 + f) for f in range(nf)]
+    Xs = [orc.forward_r2c(x) if r2c else orc.forward_c2c(x) for x in xs]
+    comms = [acc.Comm(r, nprocs, dims) for r in range(nprocs)]
+    plans = [acc.Plan(n, comms[r], r2c=r2c, single=single, wire=False, flags=acc.ACCFFT_ESTIMATE, howmany=nf) for r in range(nprocs)]
+    if nprocs > 1:
+        acc.attach_local_peers(plans)
+    assert acc.lib().accfftb_plan_howmany(plans[0]._h) == nf
+    streams = [torch.cuda.Stream() for _ in range(nprocs)]
+    ins = [[None] * nf for _ in range(nprocs)]
+    outs = [[None] * nf for _ in range(nprocs)]
+    outs1 = [[None] * nf for _ in range(nprocs)]
+    backs = [[None] * nf for _ in range(nprocs)]
+    backs1 = [[None] * nf for _ in range(nprocs)]
+    grads = [[None] * 3 for _ in range(nprocs)]
+    divs = [None] * nprocs
+    for r in range(nprocs):
+        for f in range(nf):
+            loc = orc.local_input(xs[f], n, dims, comms[r].coords).astype(rdt if r2c else cdt)
+            t = to_dev(loc, cuda_device) if loc.size else torch.zeros(2, dtype=tdt, device=cuda_device)
+            ins[r][f] = torch.view_as_real(t).contiguous() if (not r2c and loc.size) else t
+            outs[r][f] = torch.zeros(max(plans[r].alloc_max // es, 2), dtype=tdt, device=cuda_device)
+            outs1[r][f] = torch.zeros_like(outs[r][f])
+            backs[r][f] = torch.zeros_like(ins[r][f])
+            backs1[r][f] = torch.zeros_like(ins[r][f])
+        grads[r] = [torch.zeros_like(ins[r][0]) for _ in range(3)]
+        divs[r] = torch.zeros_like(ins[r][0])
+        plans[r].set_stream(streams[r].cuda_stream)
+    torch.cuda.synchronize()
+
+    def body(r):
+        p = plans[r]
+        with torch.cuda.stream(streams[r]):
+            for _ in range(2):
+                if r2c:
+                    p.execute_r2c_many(ins[r], outs[r])
+                    p.execute_c2r_many(outs[r], backs[r])
+                    for f in range(nf):
+                        p.execute_r2c(ins[r][f], outs1[r][f])
+                        p.execute_c2r(outs1[r][f], backs1[r][f])
+                else:
+                    p.execute_c2c_many(acc.ACCFFT_FORWARD, ins[r], outs[r])
+                    p.execute_c2c_many(acc.ACCFFT_BACKWARD, outs[r], backs[r])
+                    for f in range(nf):
+                        p.execute_c2c(acc.ACCFFT_FORWARD, ins[r][f], outs1[r][f])
+                        p.execute_c2c(acc.ACCFFT_BACKWARD, outs1[r][f], backs1[r][f])
+            if r2c:
+                p.grad_slow(grads[r][0], grads[r][1], grads[r][2], ins[r][0])
+                p.divergence_slow(divs[r], ins[r][0], ins[r][1], ins[r][2])
+
+    run_ranks(nprocs, body)
+    torch.cuda.synchronize()
+    for f in range(nf):
+        blocks = []
+        for r in range(nprocs):
+            osz = plans[r].osize
+            blocks.append(outs[r][f].cpu().numpy().view(cdt)[:osz[0] * osz[1] * osz[2]].reshape(osz))
+            assert torch.equal(outs[r][f], outs1[r][f]) and torch.equal(backs[r][f], backs1[r][f])
+        assert orc.rel_l2(orc.assemble_output(blocks, n, dims, r2c=r2c), Xs[f]) <= TOL[single]
+    if r2c:
+        tol = 1e-11 if not single else 2e-4
+        for ax in range(3):
+            bl = [grads[r][ax].cpu().numpy().ravel()[:int(np.prod(plans[r].isize))].reshape(plans[r].isize) for r in range(nprocs)]
+            assert orc.rel_l2(orc.assemble_input(bl, n, dims), orc.grad_slow(xs[0], ax)) <= tol
+        bl = [divs[r].cpu().numpy().ravel()[:int(np.prod(plans[r].isize))].reshape(plans[r].isize) for r in range(nprocs)]
+        assert orc.rel_l2(orc.assemble_input(bl, n, dims), orc.divergence_slow(*xs)) <= tol
+    # a plan made for fewer fields refuses the batch
+    with pytest.raises(acc.AccfftError):
+        q = make_plan((8, 8, 8), True, False)
+        try:
+            a = torch.zeros(512, dtype=torch.float64, device=cuda_device)
+            o = torch.zeros(q.alloc_max // 8, dtype=torch.float64, device=cuda_device)
+            q.execute_r2c_many([a, a], [o, o])
+        finally:
+            q.destroy()
+    for p in plans:
+        acc.lib().accfftb_plan_destroy(p._h)
+        p._h = None
