@@ -394,7 +394,7 @@ METRIC = "3D r2c+c2r GFLOP/s (5N*log2N per transform) at 512^3 double"
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512, help="grid edge (default: the headline 512)")
@@ -490,6 +490,14 @@ def main():
     # per-kernel durations for the roofline: the same args.steps steps once more, this time with an event pair around every
     # launch (accfftb_plan_set_profiling).  Kept out of the region above because the 12 extra event records per step keep
     # consecutive kernels from running back to back (measured: +3 % on the step).
+    # The pass starts like the timed region did -- after a pause and the same warm-up -- because the board's power limiter
+    # (clocks `reasons`: sw_power_cap) takes ~0.1 s of continuous load to pull the SM clock down: a pass that followed the timed
+    # region immediately would run every kernel under a lower clock than the region itself saw (measured: 8 % slower).
+    time.sleep(1.0)
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            step()
+    sync_all()
     plan.set_profiling(True)
     plan.profile_read()
     with torch.cuda.stream(stream):

@@ -9,7 +9,7 @@ if [ -z "$SKIP_TESTS" ]; then
 ( time timeout 1500 python -m pytest tests -q -m gpu --durations=8 2>&1 | tail -25 ) > gpurun_out/gpu_tests_$TAG.log 2>&1
 fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1
-timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
 timeout 600 python scripts/stage_profile.py > gpurun_out/stage_profile_$TAG.txt 2>&1
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
