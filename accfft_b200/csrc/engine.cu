@@ -298,8 +298,11 @@ struct Engine {
   bool l2_persist = false;     // ACCFFT_B200_L2_PERSIST=1: give the hand-off buffer an L2-persisting access-policy window
   size_t l2_window_max = 0;
   long long l2_budget = 0;     // ACCFFT_B200_L2_MB: bytes of intermediate planes kept L2-resident between two local passes (0: off)
-  // fused local Z / Y pair (fused.cuh): ACCFFT_B200_FUSED=1 switches it on; _CP / _LAG / _NS tune it (_FLAGS: debugging).
-  // Off by default: measured slower than the two stand-alone kernels although it halves their HBM traffic.
+  // fused local Z / Y pair (fused.cuh).  ACCFFT_B200_FUSED: 0 = never, 1 = wherever a fused kernel exists, 2 = only where the
+  // strided pass stores to peers (forward on a slab grid) and would run in the same CTA shape stand-alone; _CP / _LAG / _NS
+  // tune it (_FLAGS: debugging).  Default: 2 on multi-rank slab grids (there the Y pass is NVLink-bound and the Z tiles fill the
+  // SM time it leaves idle: 2 % on the step at 2 and at 8 GPUs, profiles/fused_n{2,8}_r2q.txt), 0 elsewhere (with both passes
+  // local it is slower than the two stand-alone kernels although it halves their HBM traffic).
   int fused_mode = 0;
   FusedTune fused_tune = {0, 0, 0, 0};
   FusedInfo fused_info[2] = {};   // what the last forward / inverse fused launch used (accfftb_plan_fused_info)
@@ -619,6 +622,9 @@ int CudaBackend::launch(const Launch& l) {
 int CudaBackend::launch_fused(const Launch& lz, const Launch& ly, bool z_first) {
   if (!lz.dry) e->fused_info[z_first ? 0 : 1] = FusedInfo{};
   if (!e->fused_mode || !e->fused_ctr) return -2;
+  // mode 2: only where the strided pass stores to peers (forward on a slab grid): there the pass is NVLink-bound and the
+  // contiguous pass's tiles fill the SM time it leaves idle
+  if (e->fused_mode == 2 && (stage_is_simple(ly.desc) || has_wide(ly.prec, ly.fftN))) return -2;
   if (e->timing && !lz.dry) return -2;   // per-stage timers of the reference-style `timer` array want separate stages
   const bool r2c = lz.kind == K_CONTIG_R2C || lz.kind == K_CONTIG_C2R;
   if (!r2c && lz.kind != K_CONTIG_C2C) return -2;
@@ -961,6 +967,7 @@ accfftb_plan* accfftb_plan_create_many(const int n[3], const int c_dims[2], int 
       e->timeout_cycles = 10LL * 1000 * (long long)khz;   // 10 seconds of SM clock
     if (const char* m = getenv("ACCFFT_B200_BARRIER_TIMEOUT_MS")) e->timeout_cycles = (long long)atoll(m) * (long long)(khz > 0 ? khz : 2000000);
   }
+  e->fused_mode = (pl.nprocs > 1 && c_dims[1] == 1) ? 2 : 0;
   if (const char* m = getenv("ACCFFT_B200_FUSED")) e->fused_mode = atoi(m);
   if (const char* m = getenv("ACCFFT_B200_FUSED_CP")) e->fused_tune.cp = atoi(m);
   if (const char* m = getenv("ACCFFT_B200_FUSED_LAG")) e->fused_tune.lag = atoi(m);
