@@ -20,24 +20,9 @@
 #include "cuda_ctx.cuh"
 #include "kernel_cfg.hpp"
 #include "launch.hpp"
+#include "fused_sched.hpp"
 
 namespace accfft_b200 {
-
-struct FusedArgs {
-  int* ctr;          // [0] work counter, [1 .. nch] pass-1 tiles done per chunk, [1 + nch .. 2 nch] pass-2 tiles done per chunk
-  int nch, cp;       // chunks, planes per chunk
-  int lag, ns;       // pass 2 runs `lag` chunks behind pass 1; ring slots (in chunks), ns > lag
-  int t1, t2;        // tiles per chunk of pass 1 / pass 2
-  int tpa;           // strided pass: tiles per plane
-  int tz;            // contiguous pass: tiles per chunk (= cp * pencils per plane / PCZ)
-  int zfirst;        // 1: pass 1 is the contiguous (Z) pass (forward), 0: the strided one (inverse)
-  int ztiles, yplanes;   // tiles of the contiguous pass / planes of the strided pass that exist (the last chunk may be ragged)
-  int flags;         // debugging: bit 0 = signal a tile's completion right away (not from the next tile's hook),
-                     //            bit 1 = no early dependency check (every tile polls)
-                     //            bit 2 = TIMING EXPERIMENT, results invalid: no dependency waits, no signals
-                     //            bit 3 = static work assignment (item = CTA + k * grid) instead of the global counter
-  long long total;   // work items = (nch + lag) * (t1 + t2)
-};
 
 __device__ __forceinline__ int fused_ld_acquire(const int* p) {
   int v;
@@ -50,18 +35,6 @@ __device__ __forceinline__ int fused_ld_relaxed(const int* p) {
   return v;
 }
 
-// what the scheduler publishes for a work item
-enum FusedKind : int { FK_END = 0, FK_DEAD = 1, FK_EMPTY = 2, FK_Z = 3, FK_Y = 4 };
-struct FusedSlot {
-  int kind;    // FK_END: list exhausted; FK_DEAD: chunk out of range, nothing to do; FK_EMPTY: a tile beyond the ragged end (signals
-               // only); FK_Z / FK_Y: run the contiguous / strided body on tile `bid`
-  int ready;   // its dependency was found satisfied by the early check
-  int bid;     // tile index in the body's own numbering
-  int sig;     // index into ctr of the counter the tile increments when done
-  int dep;     // index into ctr of the counter it waits for (0: none) ...
-  int target;  // ... and the value that counter must reach
-};
-
 // scheduler state of a CTA (shared memory; only thread 0 touches anything but `next`)
 struct FusedSched {
   FusedArgs fa;
@@ -73,40 +46,6 @@ struct FusedSched {
 __device__ __forceinline__ FusedSched& fused_sched() {
   __shared__ FusedSched ss;
   return ss;
-}
-
-__device__ __forceinline__ FusedSlot fused_decode(const FusedArgs& fa, int w) {
-  FusedSlot it;
-  it.ready = 0, it.bid = 0, it.sig = 0, it.dep = 0, it.target = 0;
-  if ((long long)w >= fa.total) {
-    it.kind = FK_END;
-    return it;
-  }
-  const int per = fa.t1 + fa.t2;
-  const int s = w / per, i = w - s * per;
-  const bool ph1 = i < fa.t1;
-  const int c = ph1 ? s : s - fa.lag;
-  const int t = ph1 ? i : i - fa.t1;
-  if (c < 0 || c >= fa.nch) {
-    it.kind = FK_DEAD;
-    return it;
-  }
-  if (ph1) {
-    it.sig = 1 + c;
-    if (c >= fa.ns) it.dep = 1 + fa.nch + (c - fa.ns), it.target = fa.t2;
-  } else {
-    it.sig = 1 + fa.nch + c;
-    it.dep = 1 + c, it.target = fa.t1;
-  }
-  const bool ztype = ph1 == (fa.zfirst != 0);
-  if (ztype) {
-    it.bid = c * fa.tz + t;
-    it.kind = it.bid < fa.ztiles ? FK_Z : FK_EMPTY;
-  } else {
-    it.bid = c * fa.cp * fa.tpa + t;
-    it.kind = it.bid / fa.tpa < fa.yplanes ? FK_Y : FK_EMPTY;
-  }
-  return it;
 }
 
 // Execution context of a tile inside the fused kernel.  Besides the ring addressing (RIN / ROUT: the stage's input / output is

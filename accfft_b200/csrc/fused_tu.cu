@@ -55,43 +55,16 @@ static int fused_launch_one(const Launch& lz, const Launch& ly, const FusedTune&
     if (geny && !FWD) return -2;
     if (C::F && dy.inStrideB != 1) return -2;
     const int nA = dz.nA;
-    // planes per chunk: a power of two (the ring is addressed with a mask) whose pencils fill whole contiguous-pass tiles
-    int cp = 1;
-    while (cp < (tune.cp > 0 ? tune.cp : 2)) cp *= 2;
-    while (cp <= 64 && ((long long)cp * dz.nB) % C::PCZ != 0) cp *= 2;
-    if (cp > 64) return -2;
     constexpr int TCE = C::F ? 2 * PairCfg<SY>::TCP : Cfg<T, SY>::TC;
-    FusedArgs fa;
-    fa.ctr = ctr;
-    fa.cp = cp;
-    fa.nch = (nA + cp - 1) / cp;
-    fa.tpa = (dy.nB + dy.colShift + TCE - 1) / TCE;
-    fa.tz = (int)(((long long)cp * dz.nB) / C::PCZ);
-    const int ty = cp * fa.tpa;
-    fa.t1 = FWD ? fa.tz : ty;
-    fa.t2 = FWD ? ty : fa.tz;
-    const int per = fa.t1 + fa.t2;
     long long grid = (long long)fused_sm_count() * C::MINB;
-    int lag = tune.lag > 0 ? tune.lag : (int)((3 * grid / 2 + per - 1) / per);
-    if (lag < 1) lag = 1;
-    int ns = tune.ns > lag ? tune.ns : lag + 2;
-    {   // ring slots: a power of two
-      int p2 = 1;
-      while (p2 < ns) p2 *= 2;
-      ns = p2;
-    }
-    fa.lag = lag;
-    fa.ns = ns;
-    fa.zfirst = FWD ? 1 : 0;
-    fa.ztiles = (int)(((long long)dz.nA * dz.nB + C::PCZ - 1) / C::PCZ);
-    fa.yplanes = dy.nA;
-    fa.flags = tune.flags;
-    if ((long long)(fa.nch + lag) * per > 0x3fffffffLL) return -2;
-    fa.total = (long long)(fa.nch + lag) * per;
-    if (1 + 2 * fa.nch > ctr_ints) return -2;
-    const long long ring = (long long)ns * cp;          // planes, a power of two
-    const int ringA = ring >= nA ? 0 : (int)ring;       // a ring as long as the array is plain addressing (mask = all ones)
-    const int mask = ringA ? ringA - 1 : 0x7fffffff;
+    FusedArgs fa;
+    FusedShape sh;
+    if (!fused_make_args(nA, dz.nB, C::PCZ, (dy.nB + dy.colShift + TCE - 1) / TCE, grid, tune.cp, tune.lag, tune.ns, tune.flags, FWD,
+                         ctr_ints, fa, sh))
+      return -2;
+    fa.ctr = ctr;
+    const int cp = sh.cp, lag = sh.lag, ns = sh.ns, ringA = sh.ring_planes;
+    const int mask = ringA ? ringA - 1 : 0x7fffffff;   // a ring as long as the array is plain addressing (mask = all ones)
     if (FWD) dz.outRing = mask, dy.inRing = mask;
     else dy.outRing = mask, dz.inRing = mask;
     if (info) {

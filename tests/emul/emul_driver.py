@@ -12,11 +12,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "_build", "libemul.so")
 NPARTS = 8
-MAIN_SOURCES = [os.path.join(HERE, "emul.cpp"), os.path.join(ROOT, "accfft_b200", "csrc", "plan.cpp")]
+MAIN_SOURCES = [os.path.join(HERE, "emul.cpp"), os.path.join(ROOT, "accfft_b200", "csrc", "plan.cpp"), os.path.join(HERE, "fused_sim.cpp")]
 PART_SOURCE = os.path.join(HERE, "emul_part.cpp")
 SOURCES = MAIN_SOURCES + [PART_SOURCE, os.path.join(HERE, "emul_fiber.hpp")]
 HEADERS = [os.path.join(ROOT, "accfft_b200", "csrc", f)
-           for f in ("fft_engine.cuh", "stage.cuh", "stage_real.cuh", "plan.hpp", "launch.hpp", "decomp.hpp", "kernel_cfg.hpp", "schedules.def")]
+           for f in ("fft_engine.cuh", "stage.cuh", "stage_real.cuh", "plan.hpp", "launch.hpp", "decomp.hpp", "kernel_cfg.hpp", "schedules.def", "fused_sched.hpp")]
 
 sys.path.insert(0, ROOT)
 from oracle import accfft_oracle as orc  # noqa: E402
@@ -70,6 +70,8 @@ def lib():
         _lib.emu_execute_xyz.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
                                          ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         pp = ctypes.POINTER(ctypes.c_void_p)
+        _lib.emu_fused_protocol_sim.restype = ctypes.c_int
+        _lib.emu_fused_protocol_sim.argtypes = [ctypes.c_int] * 9 + [ctypes.c_ulonglong, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         _lib.emu_execute_many.restype = ctypes.c_int
         _lib.emu_execute_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, pp, pp]
         _lib.emu_execute_grad.restype = ctypes.c_int
@@ -237,6 +239,14 @@ class World:
             s1 = orc.block(n[1], self.np_[1], c[1])[0]
             blocks.append(outs[r][:s0 * s1 * n[2]].reshape(s0, s1, n[2]).copy())
         return blocks
+
+
+def fused_protocol_sim(nA, nBz, PCZ, tpa, nctas, cp=0, lag=0, ns=0, zfirst=True, seed=1, flags=0):
+    """-> (rc, {"cp", "lag", "ns", "ring_planes", "chunks"}): a randomised CPU run of the fused kernel's scheduling protocol on the
+    real work-list code (tests/emul/fused_sim.cpp); rc 0 = every dependency held, every tile ran once, no deadlock"""
+    shape = (ctypes.c_int * 5)()
+    rc = lib().emu_fused_protocol_sim(nA, nBz, PCZ, tpa, nctas, cp, lag, ns, int(zfirst), seed, flags, shape)
+    return rc, dict(zip(("cp", "lag", "ns", "ring_planes", "chunks"), [int(v) for v in shape]))
 
 
 def _local_real(w, x_global):
