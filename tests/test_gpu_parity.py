@@ -70,7 +70,9 @@ SIZES = [(8, 8, 8), (16, 12, 20), (2, 2, 2), (4, 6, 10), (5, 3, 8), (32, 48, 64)
          (135, 270, 6), (375, 4, 540), (8, 675, 750), (1080, 6, 4), (4, 1125, 6), (6, 4, 1350), (864, 4, 6), (450, 6, 4),
          # prime radices 7 / 11 / 13, the composite 14, and 4096-long axes (three radix-16 passes, 256 threads per column)
          (7, 14, 22), (49, 13, 26), (28, 44, 98), (448, 6, 56), (6, 1792, 8), (4, 6, 896), (12, 10, 14),
-         (4096, 4, 6), (6, 4096, 4), (4, 6, 8192)]
+         (4096, 4, 6), (6, 4096, 4), (4, 6, 8192),
+         # N2 = 384: the contiguous kernels run 192 points with a warp per pencil (schedules.def: KEEP_C), partly idle passes
+         (6, 10, 384), (20, 12, 192)]
 
 
 @pytest.mark.parametrize("n", SIZES)
