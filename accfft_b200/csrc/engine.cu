@@ -624,7 +624,8 @@ int CudaBackend::launch_fused(const Launch& lz, const Launch& ly, bool z_first) 
   if (!e->fused_mode || !e->fused_ctr) return -2;
   // mode 2: only where the strided pass stores to peers (forward on a slab grid): there the pass is NVLink-bound and the
   // contiguous pass's tiles fill the SM time it leaves idle
-  if (e->fused_mode == 2 && (stage_is_simple(ly.desc) || has_wide(ly.prec, ly.fftN))) return -2;
+  // (measured for r2c plans only -- c2c tiles are twice the size and lose more inside the persistent loop: not fused in mode 2)
+  if (e->fused_mode == 2 && (stage_is_simple(ly.desc) || has_wide(ly.prec, ly.fftN) || lz.kind != K_CONTIG_R2C)) return -2;
   if (e->timing && !lz.dry) return -2;   // per-stage timers of the reference-style `timer` array want separate stages
   const bool r2c = lz.kind == K_CONTIG_R2C || lz.kind == K_CONTIG_C2R;
   if (!r2c && lz.kind != K_CONTIG_C2C) return -2;
