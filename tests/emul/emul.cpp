@@ -36,6 +36,20 @@ bool emu_launch_part_4(const Launch&);
 bool emu_launch_part_5(const Launch&);
 bool emu_launch_part_6(const Launch&);
 bool emu_launch_part_7(const Launch&);
+// per-kind / per-precision schedules of the contiguous kernels (emul_alt.cpp; mirrors k_tu.cu kinds 1, 2, 3)
+bool emu_launch_alt_k1_p0(const Launch&);
+bool emu_launch_alt_k1_p1(const Launch&);
+bool emu_launch_alt_k2_p0(const Launch&);
+bool emu_launch_alt_k2_p1(const Launch&);
+bool emu_launch_alt_k3_p0(const Launch&);
+bool emu_launch_alt_k3_p1(const Launch&);
+int emu_alt_count_k1_p0();
+int emu_alt_count_k1_p1();
+int emu_alt_count_k2_p0();
+int emu_alt_count_k2_p1();
+int emu_alt_count_k3_p0();
+int emu_alt_count_k3_p1();
+static long long g_alt_launches = 0;
 static_assert(EMU_NPARTS == 8, "emul.cpp declares eight parts");
 
 static bool emu_supported(int N) {
@@ -70,6 +84,17 @@ static void emu_launch(const Launch& l) {
     if (l.prec == PREC_DOUBLE) emu_copy_stage<double>(l);
     else emu_copy_stage<float>(l);
     return;
+  }
+  {   // the schedule the CUDA build gives this kind / precision, where it has its own
+    bool alt = false;
+    const bool dbl = l.prec == PREC_DOUBLE;
+    if (l.kind == K_CONTIG_C2C) alt = dbl ? emu_launch_alt_k1_p0(l) : emu_launch_alt_k1_p1(l);
+    else if (l.kind == K_CONTIG_R2C) alt = dbl ? emu_launch_alt_k2_p0(l) : emu_launch_alt_k2_p1(l);
+    else if (l.kind == K_CONTIG_C2R) alt = dbl ? emu_launch_alt_k3_p0(l) : emu_launch_alt_k3_p1(l);
+    if (alt) {
+      __atomic_add_fetch(&g_alt_launches, 1, __ATOMIC_RELAXED);
+      return;
+    }
   }
   if (emu_launch_part_0(l) || emu_launch_part_1(l) || emu_launch_part_2(l) || emu_launch_part_3(l) || emu_launch_part_4(l) ||
       emu_launch_part_5(l) || emu_launch_part_6(l) || emu_launch_part_7(l))
@@ -224,6 +249,14 @@ void emu_world_destroy(void* h) {
   pthread_barrier_destroy(&w->bar);
   delete w;
 }
+
+// lengths with a kind- / precision-specific schedule (sum over the six contiguous kernel kinds x precisions), and how many
+// stage launches have used one so far
+int emu_alt_schedule_count() {
+  return emu_alt_count_k1_p0() + emu_alt_count_k1_p1() + emu_alt_count_k2_p0() + emu_alt_count_k2_p1() + emu_alt_count_k3_p0() +
+         emu_alt_count_k3_p1();
+}
+long long emu_alt_launches() { return g_alt_launches; }
 
 long long emu_alloc_max(void* h, int rank) { return ((EmuWorld*)h)->plans[rank].g.L.alloc_max; }
 

@@ -14,7 +14,8 @@ LIB = os.path.join(HERE, "_build", "libemul.so")
 NPARTS = 8
 MAIN_SOURCES = [os.path.join(HERE, "emul.cpp"), os.path.join(ROOT, "accfft_b200", "csrc", "plan.cpp"), os.path.join(HERE, "fused_sim.cpp")]
 PART_SOURCE = os.path.join(HERE, "emul_part.cpp")
-SOURCES = MAIN_SOURCES + [PART_SOURCE, os.path.join(HERE, "emul_fiber.hpp")]
+ALT_SOURCE = os.path.join(HERE, "emul_alt.cpp")   # kind- / precision-specific schedules of the contiguous kernels
+SOURCES = MAIN_SOURCES + [PART_SOURCE, ALT_SOURCE, os.path.join(HERE, "emul_fiber.hpp")]
 HEADERS = [os.path.join(ROOT, "accfft_b200", "csrc", f)
            for f in ("fft_engine.cuh", "stage.cuh", "stage_real.cuh", "plan.hpp", "launch.hpp", "decomp.hpp", "kernel_cfg.hpp", "schedules.def", "fused_sched.hpp")]
 
@@ -39,6 +40,11 @@ def build(force=False):
         o = os.path.join(bdir, "part%d.o" % k)
         objs.append(o)
         jobs.append(subprocess.Popen(["g++", *flags, "-DEMU_PART=%d" % k, "-c", PART_SOURCE, "-o", o]))
+    for kind in (1, 2, 3):
+        for prec in (0, 1):
+            o = os.path.join(bdir, "alt_k%d_p%d.o" % (kind, prec))
+            objs.append(o)
+            jobs.append(subprocess.Popen(["g++", *flags, "-DEMU_ALT_KIND=%d" % kind, "-DEMU_ALT_PREC=%d" % prec, "-c", ALT_SOURCE, "-o", o]))
     for i, src in enumerate(MAIN_SOURCES):
         o = os.path.join(bdir, "main%d.o" % i)
         objs.append(o)
@@ -70,6 +76,8 @@ def lib():
         _lib.emu_execute_xyz.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
                                          ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         pp = ctypes.POINTER(ctypes.c_void_p)
+        _lib.emu_alt_schedule_count.restype = ctypes.c_int
+        _lib.emu_alt_launches.restype = ctypes.c_longlong
         _lib.emu_fused_protocol_sim.restype = ctypes.c_int
         _lib.emu_fused_protocol_sim.argtypes = [ctypes.c_int] * 9 + [ctypes.c_ulonglong, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         _lib.emu_execute_many.restype = ctypes.c_int

@@ -335,3 +335,26 @@ def test_batched_fields_share_the_exchanges(monkeypatch, n, np_, r2c):
         dv = emu.divergence(w, *xs)
         assert orc.rel_l2(orc.assemble_input(dv, n, np_), orc.divergence_slow(*xs)) < 1e-12
     w.close()
+
+
+@pytest.mark.parametrize("n,np_,single", [((6, 10, 384), (1, 1), False), ((12, 8, 384), (2, 2), False), ((6, 10, 384), (1, 2), True),
+                                          ((8, 6, 512), (1, 1), True), ((10, 12, 256), (2, 1), True), ((4, 6, 1024), (1, 1), True),
+                                          ((6, 8, 768), (1, 1), True)])
+def test_contiguous_kernels_run_the_gpu_builds_own_schedules(n, np_, single):
+    """schedules.def gives the contiguous (Z pass) kernels their own schedules for some lengths (KEEP_C: a warp per pencil at 192
+    points; KEEP_FC: 16 values per thread in single precision); tests/emul/emul_alt.cpp instantiates exactly those lines, so the
+    Z stages below run what the GPU runs -- incl. passes in which part of a pencil's threads idle"""
+    assert emu.lib().emu_alt_schedule_count() >= 9
+    before = emu.lib().emu_alt_launches()
+    x = orc.synthetic_real(n, 33)
+    X = orc.forward_r2c(x)
+    w = emu.World(n, np_, r2c=True, single=single)
+    tol = 1e-5 if single else 1e-12
+    assert orc.rel_l2(orc.assemble_output(w.forward(x), n, np_), X) < tol
+    assert orc.rel_l2(orc.assemble_input(w.inverse(X), n, np_), x * x.size) < tol
+    w.close()
+    assert emu.lib().emu_alt_launches() > before, "the Z stages did not pick a kind-specific schedule"
+    z = orc.synthetic_complex((n[0], n[1], n[2] // 2), 34)
+    w = emu.World((n[0], n[1], n[2] // 2), np_, r2c=False, single=single)
+    assert orc.rel_l2(orc.assemble_output(w.forward(z), z.shape, np_, r2c=False), orc.forward_c2c(z)) < tol
+    w.close()
